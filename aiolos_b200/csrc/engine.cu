@@ -1,0 +1,441 @@
+// Ensemble engine: owns the device state of `ncol` independent columns and advances them by launching the fused
+// per-column kernels (hydro.cuh, friction.cuh, rad_simple.cuh, rad_full.cuh) on one CUDA stream.
+// One time step of every still-active column = one launch sequence  k_hydro -> [k_friction] -> [k_rad_*],
+// i.e. c_Sim::execute()'s loop body (reference advection.cpp:60-348) with one CTA per column.
+#include "engine.h"
+#include "common.cuh"
+#include "hydro.cuh"
+#include "friction.cuh"
+#include "rad_simple.cuh"
+#include "rad_full.cuh"
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace aio {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    std::ostringstream os_; os_ << "CUDA error " << cudaGetErrorString(e_) << " at " << __FILE__ << ":" << __LINE__; \
+    throw std::runtime_error(os_.str()); } } while (0)
+
+struct Engine::Impl {
+    DevParams p{};
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int NT = 256, CPT = 4;
+    size_t smem_hydro = 0, smem_rad = 0, smem_fric = 0;
+    int nt_full = 0; size_t smem_full = 0;
+    bool has_friction = false;
+    long long launches = 0;
+    std::vector<ColState> h_cs;
+    double* pinned = nullptr; size_t pinned_bytes = 0;
+    double* d_mass = nullptr;
+
+    template <typename T> T* dalloc(size_t n) {
+        void* q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T))); allocs.push_back(q);
+        CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), stream)); return (T*)q;
+    }
+    template <typename T> T* upload(const std::vector<T>& v) {
+        T* d = dalloc<T>(v.size());
+        if (!v.empty()) CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return d;
+    }
+    double* pin(size_t bytes) {
+        if (bytes > pinned_bytes) { if (pinned) cudaFreeHost(pinned); CK(cudaMallocHost(&pinned, bytes)); pinned_bytes = bytes; }
+        return pinned;
+    }
+};
+
+// phi as the first update_mass_and_pot() call of execute() leaves it (reference source.cpp:50-109): cells 2..N are
+// recomputed with star_mass and a cubed semi-major axis, cells 0,1,N+1 keep the values of init_grav_pot + BC edits.
+static void phi_after_first_update(const Problem& q, std::vector<double>& phi) {
+    const double G = 6.678e-8, au = 1.495978707e13;
+    double rs_at_moment = q.rs;   // globalTime(0) < rs_time is rejected at create time
+    for (int i = 2; i <= q.num_cells; i++) {
+        double r = q.x_i12[i], mass = q.planet_mass, ph;
+        if (q.use_linear_gravity) ph = -G * mass * std::abs(q.domain_max - r);
+        else if (std::abs(r - q.planet_position) > rs_at_moment) ph = -G * mass / std::abs(r - q.planet_position);
+        else ph = -G * mass * (pow(r - q.planet_position, 3.) / pow(rs_at_moment, 4.) - 2. * pow(r - q.planet_position, 2.) / pow(rs_at_moment, 3.) + 2. / rs_at_moment);
+        if (q.use_tides == 1) {
+            double d3 = q.planet_semimajor * au;
+            d3 = d3 * d3 * d3;
+            ph -= 0.5 * 3. * G * q.star_mass * q.x_i12[i] * q.x_i12[i] / d3;
+        }
+        phi[i] = ph;
+    }
+}
+
+static void check_supported(const Problem& q) {
+    auto fail = [](const std::string& m) { throw std::runtime_error("unsupported configuration: " + m); };
+    if (q.num_species < 1 || q.num_species > MAXS) fail("num_species outside 1.." + std::to_string(MAXS));
+    if (q.num_bands_in > MAXB || q.num_bands_out > MAXB) fail("more than 32 radiation bands");
+    if (q.num_cells < 6) fail("fewer than 6 cells");
+    if (!q.do_hydrodynamics || q.start_hydro_time > 0) fail("DO_HYDRO 0 / START_HYDRO_TIME");
+    if (q.use_self_gravity) fail("PARI_SELF_GRAV_SWITCH 1");
+    if (q.rs_time > 0) fail("PARI_SMOOTHING_TIME > 0 (time-dependent potential)");
+    if (q.K_zz_init != 0) fail("KZZ_INIT != 0");
+    if (q.photochemistry_level != 0) fail("PHOTOCHEM_LEVEL != 0 (SURVEY 8 f1: next)");
+    if (q.use_drag_predictor_step) fail("PARI_SECONDORDER_DRAG 1");
+    if (q.use_total_pressure) fail("USE_TOTAL_PRESSURE 1");
+    if (q.use_convective_fluxes) fail("USE_CONVECTION 1");
+    if (q.use_planetary_temperature) fail("USE_PLANET_TEMPERATURE 1");
+    if (q.radiation_matter_equilibrium_test != 0) fail("RAD_MATTER_EQUI_TEST != 0");
+    if (q.use_rad_fluxes < 0 || q.use_rad_fluxes > 2) fail("PARI_USE_RADIATION outside 0..2");
+    if (q.use_rad_fluxes == 2 && q.num_bands_out != 1) fail("simple FLD solver needs NUM_BANDS_OUT 1");
+    if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating) fail("simple FLD + collisional heating with >1 species");
+    if (q.use_rad_fluxes && q.opacity_model != 'C' && q.opacity_model != 'P') fail(std::string("opacity model ") + q.opacity_model);
+    if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
+    if (q.use_avg_temperature) fail("USE_AVG_T 1");
+    if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
+    for (auto& sp : q.species) {
+        if (sp.boundary_left == 0 || sp.boundary_right == 0) fail("user boundary hooks (compile a problem plugin, INTEGRATION.md)");
+    }
+}
+
+Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
+    if (cols.empty()) throw std::runtime_error("empty ensemble");
+    const Problem& q0 = cols[0];
+    check_supported(q0);
+    for (auto& q : cols) {
+        if (q.num_cells != q0.num_cells || q.num_species != q0.num_species || q.num_bands_in != q0.num_bands_in ||
+            q.num_bands_out != q0.num_bands_out || q.order != q0.order || q.x_i != q0.x_i)
+            throw std::runtime_error("ensemble columns must share grid, species count and band layout");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device: aiolos_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&im->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&im->ev0)); CK(cudaEventCreate(&im->ev1));
+    prob0 = q0;
+    DevParams& p = im->p;
+    const int N = q0.num_cells, N2 = N + 2, NP = (N2 + 31) / 32 * 32, S = q0.num_species, ncol = (int)cols.size();
+    p.N = N; p.N2 = N2; p.NP = NP; p.S = S; p.Bin = q0.num_bands_in; p.Bout = q0.num_bands_out; p.ng = q0.num_ghosts; p.ncol = ncol;
+    p.order = q0.order; p.geometry = q0.geometry; p.problem_number = q0.problem_number;
+    p.use_rad_fluxes = q0.use_rad_fluxes; p.friction_solver = q0.friction_solver;
+    p.use_collisional_heating = q0.use_collisional_heating; p.photochemistry_level = q0.photochemistry_level;
+    p.closed_radiative_boundaries = q0.closed_radiative_boundaries; p.use_planetary_temperature = q0.use_planetary_temperature;
+    p.couple_J_into_T = q0.couple_J_into_T; p.solve_for_j = q0.solve_for_j;
+    p.radiation_matter_equilibrium_test = q0.radiation_matter_equilibrium_test; p.use_total_pressure = q0.use_total_pressure;
+    p.collision_model = q0.collision_model; p.opacity_model = q0.opacity_model;
+    im->has_friction = (q0.friction_solver >= 0 && S > 1);     // compute_drag_update, source.cpp:233-243
+    p.last_kernel = q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
+    p.max_timestep_change = q0.max_timestep_change; p.dt_min_init = q0.dt_min_init; p.dt_max = q0.dt_max;
+    p.energy_epsilon = q0.energy_epsilon; p.CFL_break_time = q0.CFL_break_time;
+    p.right_extrap_press_multiplier = q0.right_extrap_press_multiplier; p.max_mdot = q0.max_mdot; p.planet_mass = q0.planet_mass;
+    p.alpha_collision = q0.alpha_collision; p.alpha_collision_ions = q0.alpha_collision_ions;
+    p.coll_rampup_time = q0.coll_rampup_time; p.init_coll_factor = q0.init_coll_factor;
+    p.radiation_rampup_time = q0.radiation_rampup_time; p.init_radiation_factor = q0.init_radiation_factor;
+    p.bond_albedo = q0.bond_albedo; p.xi_rad = q0.xi_rad; p.no_rad_trans = q0.no_rad_trans;
+    p.photocooling_expansion = q0.photocooling_expansion; p.temperature_floor = q0.temperature_floor; p.max_temperature = q0.max_temperature;
+    p.kS_factor = q0.const_opacity_solar_factor; p.kR_factor = q0.const_opacity_rosseland_factor; p.kP_factor = q0.const_opacity_planck_factor;
+    p.T_int = q0.T_int; p.core_cv = q0.core_cv; p.lT_spacing = q0.lT_spacing; p.num_plancks = q0.num_plancks;
+    p.photon_energy0 = q0.photon_energies.empty() ? 1 : q0.photon_energies[0];
+    p.step_limit = 0;
+
+    auto padded = [&](const std::vector<double>& v) { std::vector<double> w(NP, 0.0); for (size_t i = 0; i < v.size() && i < (size_t)NP; i++) w[i] = v[i]; return w; };
+    p.x_i = im->upload(padded(q0.x_i)); p.x_i12 = im->upload(padded(q0.x_i12)); p.x_iVC = im->upload(padded(q0.x_iVC));
+    p.dx = im->upload(padded(q0.dx)); p.surf = im->upload(padded(q0.surf)); p.vol = im->upload(padded(q0.vol));
+    p.omegaplus = im->upload(padded(q0.omegaplus)); p.omegaminus = im->upload(padded(q0.omegaminus));
+    p.spp_left = im->upload(padded(q0.source_pressure_prefactor_left)); p.spp_right = im->upload(padded(q0.source_pressure_prefactor_right));
+    p.planck_matrix = im->upload(q0.planck_matrix); p.l_i_out = im->upload(q0.l_i_out);
+    p.highenergy_switch = im->upload(q0.highenergy_switch);
+    p.fric_mask = im->upload(q0.friction_coeff_mask); p.inv_totmasses = im->upload(q0.inv_totmasses);
+    p.resonant_pair = im->upload(q0.resonant_pair_matrix);
+
+    // species constants + band-mean opacities with the model factors folded in (update_opacities, opacities.cpp:110-134,328-347)
+    std::vector<SpeciesConst> sc(S);
+    const int KA = p.Bin + 2 * p.Bout;
+    std::vector<double> kap((size_t)S * KA, 0.0);
+    for (int s = 0; s < S; s++) {
+        const SpeciesData& d = q0.species[s];
+        SpeciesConst& c = sc[s];
+        memset(&c, 0, sizeof c);
+        c.gm1 = 2. / d.degrees_of_freedom; c.cv = d.cv; c.mass = d.mass_amu * 1.66054e-24; c.mass_amu = d.mass_amu; c.inv_mass = d.inv_mass;
+        c.gamma_adiabat = d.gamma_adiabat; c.static_charge = d.static_charge; c.const_T_space = d.const_T_space; c.const_opacity = d.const_opacity;
+        c.wave_amplitude = d.WAVE_AMPLITUDE; c.wave_period = d.WAVE_PERIOD; c.use_wave = d.USE_WAVE;
+        for (int k = 0; k < 3; k++) { c.shock_ul[k] = d.SHOCK_TUBE_UL[k]; c.shock_ur[k] = d.SHOCK_TUBE_UR[k]; c.background_u[k] = d.BACKGROUND_U[k]; }
+        c.is_dust_like = d.is_dust_like; c.bc_left = d.boundary_left; c.bc_right = d.boundary_right;
+        c.prim2_speed = d.prim2_speed_init.empty() ? 0 : d.prim2_speed_init[0];
+        for (int b = 0; b < p.Bin; b++) {
+            double a = b < (int)d.opacity_avg_solar.size() ? d.opacity_avg_solar[b] : 0;
+            kap[(size_t)s * KA + b] = (q0.opacity_model == 'P' && d.is_dust_like) ? a : q0.const_opacity_solar_factor * a;
+        }
+        for (int b = 0; b < p.Bout; b++) {
+            double kp, kr;
+            if (q0.opacity_model == 'P') {
+                double ap = b < (int)d.opacity_avg_planck.size() ? d.opacity_avg_planck[b] : 0;
+                double ar = b < (int)d.opacity_avg_rosseland.size() ? d.opacity_avg_rosseland[b] : 0;
+                kp = d.is_dust_like ? ap : q0.const_opacity_planck_factor * ap;
+                kr = d.is_dust_like ? ar : q0.const_opacity_rosseland_factor * ar;
+            } else {
+                kp = q0.const_opacity_planck_factor * d.const_opacity;
+                kr = q0.const_opacity_rosseland_factor * d.const_opacity;
+            }
+            kap[(size_t)s * KA + p.Bin + b] = kp;
+            kap[(size_t)s * KA + p.Bin + p.Bout + b] = kr;
+        }
+    }
+    p.sp = im->upload(sc);
+    p.kappa_avg = im->upload(kap);
+
+    // per-column state
+    std::vector<double> hu((size_t)3 * ncol * S * NP, 0.0), he((size_t)ncol * S * NP, 0.0), hphi((size_t)ncol * NP, 0.0);
+    std::vector<double> hphis((size_t)ncol * S * NP, 0.0), hJ((size_t)ncol * p.Bout * NP, 0.0), hsol((size_t)ncol * p.Bin, 0.0);
+    std::vector<double> hp2((size_t)ncol * S, 0.0);
+    im->h_cs.assign(ncol, ColState{});
+    for (int c = 0; c < ncol; c++) {
+        const Problem& q = cols[c];
+        std::vector<double> phi = q.phi;
+        phi_after_first_update(q, phi);
+        for (int j = 0; j < N2; j++) hphi[idx_c(p, c, j)] = phi[j];
+        for (int s = 0; s < S; s++) {
+            const SpeciesData& d = q.species[s];
+            for (int j = 0; j < N2; j++) {
+                hu[idx_u(p, 0, c, s, j)] = d.u1[j]; hu[idx_u(p, 1, c, s, j)] = d.u2[j]; hu[idx_u(p, 2, c, s, j)] = d.u3[j];
+                he[idx_s(p, c, s, j)] = d.eint_last[j];
+                hphis[idx_s(p, c, s, j)] = phi[j];
+            }
+            for (int j = N2; j < NP; j++) { hu[idx_u(p, 0, c, s, j)] = 1; hu[idx_u(p, 2, c, s, j)] = 1; }
+            hp2[(size_t)c * S + s] = d.prim2_speed_init.empty() ? 0 : d.prim2_speed_init[0];
+        }
+        for (int b = 0; b < p.Bout; b++) for (int j = 0; j < N2; j++) hJ[idx_J(p, c, b, j)] = q.Jrad_FLD[(size_t)j * p.Bout + b];
+        for (int b = 0; b < p.Bin; b++) hsol[(size_t)c * p.Bin + b] = q.solar_heating_final[b];
+        ColState& st = im->h_cs[c];
+        st.t = 0; st.dt = q.dt; st.cflfactor = q.cflfactor; st.timestep_rad2 = q.timestep_rad2; st.t_max = q.t_max;
+        st.T_planet = q.T_planet; st.steps = 0; st.status = COL_OK;
+    }
+    p.u = im->upload(hu); p.eint = im->upload(he); p.phi = im->upload(hphi); p.phis = im->upload(hphis);
+    p.J = im->upload(hJ); p.solar_heating_final = im->upload(hsol); p.prim2v = im->upload(hp2);
+    p.dS = im->dalloc<double>((size_t)ncol * S * NP);
+    {   // dS_band(N, b) as the constructor left it: the first update_dS copies it into cell N+1 (radiation.cpp:263-265)
+        std::vector<double> top((size_t)ncol * p.Bin, 0.0);
+        for (int c = 0; c < ncol; c++)
+            for (int b = 0; b < p.Bin; b++)
+                if (cols[c].dS_band.size() == (size_t)N2 * p.Bin) top[(size_t)c * p.Bin + b] = cols[c].dS_band[(size_t)N * p.Bin + b];
+        p.dSband_top = im->upload(top);
+    }
+    p.Tsave = nullptr; p.cssave = nullptr;
+    if (im->has_friction && p.use_rad_fluxes) {
+        p.Tsave = im->dalloc<double>((size_t)ncol * S * NP);
+        p.cssave = im->dalloc<double>((size_t)ncol * S * NP);
+    }
+    p.cs = im->upload(im->h_cs);
+    full_setup();
+
+    // launch geometry: NT threads per column, CPT cells per thread
+    int NT = 256;
+    if (N2 <= 32) NT = 32; else if (N2 <= 64) NT = 64; else if (N2 <= 128) NT = 128;
+    int CPT = (N2 + NT - 1) / NT;
+    if (CPT > 8) throw std::runtime_error("unsupported configuration: more than 2046 cells per column");
+    if (CPT == 3) CPT = 4; if (CPT > 4) CPT = 8;
+    im->NT = NT; im->CPT = CPT;
+    im->smem_hydro = ((size_t)9 * N2 + 32 + 12 * p.ng) * sizeof(double);
+    im->smem_rad = ((size_t)(5 * S + 7) * N2 + 32) * sizeof(double);
+    im->smem_fric = 64 * sizeof(double);
+    int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
+        throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
+#define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
+    SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
+    if (p.use_rad_fluxes == 2) { SETSM(k_rad_simple<1>, im->smem_rad); SETSM(k_rad_simple<2>, im->smem_rad); SETSM(k_rad_simple<4>, im->smem_rad); SETSM(k_rad_simple<8>, im->smem_rad); }
+#undef SETSM
+    AIO_LAUNCH(k_prime, ncol, 256, 0, im->stream, p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(im->stream));
+}
+
+Engine::~Engine() {
+    if (!im) return;
+    for (void* q : im->allocs) cudaFree(q);
+    if (im->pinned) cudaFreeHost(im->pinned);
+    if (im->ev0) cudaEventDestroy(im->ev0);
+    if (im->ev1) cudaEventDestroy(im->ev1);
+    if (im->stream) cudaStreamDestroy(im->stream);
+    delete im;
+}
+
+int Engine::ncol() const { return im->p.ncol; }
+int Engine::num_cells() const { return im->p.N; }
+int Engine::num_species() const { return im->p.S; }
+int Engine::num_bands_out() const { return im->p.Bout; }
+int Engine::num_bands_in() const { return im->p.Bin; }
+long long Engine::kernel_launches() const { return im->launches; }
+void* Engine::stream() const { return (void*)im->stream; }
+
+void Engine::launch_step() {
+    DevParams& p = im->p;
+    const int ncol = p.ncol, NT = im->NT;
+    switch (im->CPT) {
+    case 1: AIO_LAUNCH(k_hydro<1>, ncol, NT, im->smem_hydro, im->stream, p); break;
+    case 2: AIO_LAUNCH(k_hydro<2>, ncol, NT, im->smem_hydro, im->stream, p); break;
+    case 4: AIO_LAUNCH(k_hydro<4>, ncol, NT, im->smem_hydro, im->stream, p); break;
+    default: AIO_LAUNCH(k_hydro<8>, ncol, NT, im->smem_hydro, im->stream, p); break;
+    }
+    im->launches++;
+    if (im->has_friction) { launch_friction(); im->launches++; }
+    if (p.use_rad_fluxes == 2) {
+        switch (im->CPT) {
+        case 1: AIO_LAUNCH(k_rad_simple<1>, ncol, NT, im->smem_rad, im->stream, p); break;
+        case 2: AIO_LAUNCH(k_rad_simple<2>, ncol, NT, im->smem_rad, im->stream, p); break;
+        case 4: AIO_LAUNCH(k_rad_simple<4>, ncol, NT, im->smem_rad, im->stream, p); break;
+        default: AIO_LAUNCH(k_rad_simple<8>, ncol, NT, im->smem_rad, im->stream, p); break;
+        }
+        im->launches++;
+    } else if (p.use_rad_fluxes == 1) { launch_full(); im->launches++; }
+}
+
+// Advance every column by up to `nsteps` further steps (columns that reach their t_max or crash stop earlier).
+double Engine::advance(long long nsteps, bool timed) {
+    DevParams& p = im->p;
+    p.step_limit += nsteps;     // columns are bounded by their own step counters: min(steps so far) + nsteps would
+                                // desynchronise the ensemble; a global ceiling keeps "advance(k)" = k steps for all
+    // step_limit is an absolute ceiling on ColState.steps
+    if (timed) CK(cudaEventRecord(im->ev0, im->stream));
+    for (long long k = 0; k < nsteps; k++) launch_step();
+    CK(cudaGetLastError());
+    float ms = 0;
+    if (timed) { CK(cudaEventRecord(im->ev1, im->stream)); CK(cudaEventSynchronize(im->ev1)); CK(cudaEventElapsedTime(&ms, im->ev0, im->ev1)); }
+    else CK(cudaStreamSynchronize(im->stream));
+    return ms;
+}
+
+// Run until every column has finished (t >= t_max or crashed), polling the per-column clocks every `chunk` steps.
+long long Engine::run_to_tmax(long long chunk, long long max_total) {
+    long long done = 0;
+    while (done < max_total) {
+        advance(chunk, false);
+        done += chunk;
+        fetch_states();
+        bool any = false;
+        for (auto& c : im->h_cs) if (c.status == COL_OK && c.t < c.t_max) { any = true; break; }
+        if (!any) break;
+    }
+    return done;
+}
+
+void Engine::fetch_states() {
+    CK(cudaMemcpyAsync(im->h_cs.data(), im->p.cs, im->h_cs.size() * sizeof(ColState), cudaMemcpyDeviceToHost, im->stream));
+    CK(cudaStreamSynchronize(im->stream));
+}
+void Engine::push_states() {
+    CK(cudaMemcpyAsync(im->p.cs, im->h_cs.data(), im->h_cs.size() * sizeof(ColState), cudaMemcpyHostToDevice, im->stream));
+    CK(cudaStreamSynchronize(im->stream));
+}
+void Engine::set_tmax(int col, double t_max) {
+    fetch_states();
+    for (int c = 0; c < im->p.ncol; c++) if (col < 0 || c == col) im->h_cs[c].t_max = t_max;
+    push_states();
+}
+void Engine::clamp_tmax(double t_stop) {
+    fetch_states();
+    for (auto& c : im->h_cs) if (t_stop < c.t_max) c.t_max = t_stop;
+    push_states();
+}
+void Engine::set_option(const std::string& key, const std::string& value) {
+    if (key == "tridiag") {
+        if (value == "thomas") im->p.tridiag_serial = 1;
+        else if (value == "pcr") im->p.tridiag_serial = 0;
+        else throw std::invalid_argument("option tridiag: expected 'pcr' or 'thomas'");
+    } else throw std::invalid_argument("unknown option '" + key + "'");
+}
+long long Engine::total_steps() {
+    fetch_states();
+    long long n = 0;
+    for (auto& c : im->h_cs) n += c.steps;
+    return n;
+}
+void Engine::status(int col, double* t, double* dt, long long* steps, int* state) {
+    fetch_states();
+    const ColState& c = im->h_cs.at(col);
+    if (t) *t = c.t; if (dt) *dt = c.dt; if (steps) *steps = c.steps; if (state) *state = c.status;
+}
+void Engine::status_all(double* t, double* dt, long long* steps, int* state) {
+    fetch_states();
+    for (int c = 0; c < im->p.ncol; c++) {
+        const ColState& s = im->h_cs[c];
+        if (t) t[c] = s.t; if (dt) dt[c] = s.dt; if (steps) steps[c] = s.steps; if (state) state[c] = s.status;
+    }
+}
+double Engine::col_scalar(int col, int which) {
+    fetch_states();
+    const ColState& c = im->h_cs.at(col);
+    switch (which) { case 0: return c.cflfactor; case 1: return c.timestep_rad2; case 2: return c.cfl_step;
+                     case 3: return c.minstep; case 4: return c.maxde; case 5: return c.t_max; default: return 0; }
+}
+
+// field ids: include/aiolos_b200.h (AIO_F_*); names follow the reference's members
+void Engine::get_field(int col, int species, int field, double* dst, int n) {
+    DevParams& p = im->p;
+    if (col < 0 || col >= p.ncol || n > p.N2) throw std::invalid_argument("get_field: bad column or length");
+    const bool per_species = (field <= 3) || (field >= 5 && field <= 9);
+    if (per_species && (species < 0 || species >= p.S)) throw std::invalid_argument("get_field: bad species");
+    auto fetch = [&](const double* src, double* d) {
+        CK(cudaMemcpyAsync(d, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, im->stream));
+        CK(cudaStreamSynchronize(im->stream));
+    };
+    if (field >= 0 && field <= 2) fetch(p.u + idx_u(p, field, col, species, 0), dst);
+    else if (field == 3) fetch(p.eint + idx_s(p, col, species, 0), dst);
+    else if (field == 4) fetch(p.phi + idx_c(p, col, 0), dst);
+    else if (field == 5) fetch(p.phis + idx_s(p, col, species, 0), dst);
+    else if (field == 6) fetch(p.dS + idx_s(p, col, species, 0), dst);
+    else if (field >= 7 && field <= 9) {            // primitives derived from u with the EOS of eos.cpp:19-63
+        std::vector<double> a(n), b(n), c(n);
+        fetch(p.u + idx_u(p, 0, col, species, 0), a.data());
+        fetch(p.u + idx_u(p, 1, col, species, 0), b.data());
+        fetch(p.u + idx_u(p, 2, col, species, 0), c.data());
+        const SpeciesData& d = prob0.species[species];
+        const double gm1 = 2. / d.degrees_of_freedom;
+        for (int j = 0; j < n; j++) {
+            const double v = b[j] / a[j], pr = gm1 * (c[j] - 0.5 * b[j] * v);
+            dst[j] = (field == 9) ? v : (field == 8) ? pr : ((pr / a[j]) / gm1) / d.cv;
+        }
+    }
+    else if (field >= 16 && field < 16 + p.Bout) fetch(p.J + idx_J(p, col, field - 16, 0), dst);
+    else throw std::invalid_argument("get_field: unknown field id");
+}
+
+// Replace the conserved state of all columns from / copy it to host buffers laid out [3][ncol][S][N+2] (e2e path).
+void Engine::upload_u(const double* src) {
+    DevParams& p = im->p;
+    const size_t rows = (size_t)3 * p.ncol * p.S;
+    CK(cudaMemcpy2DAsync(p.u, (size_t)p.NP * sizeof(double), src, (size_t)p.N2 * sizeof(double), (size_t)p.N2 * sizeof(double), rows,
+                         cudaMemcpyHostToDevice, im->stream));
+}
+void Engine::download_u(double* dst) {
+    DevParams& p = im->p;
+    const size_t rows = (size_t)3 * p.ncol * p.S;
+    CK(cudaMemcpy2DAsync(dst, (size_t)p.N2 * sizeof(double), p.u, (size_t)p.NP * sizeof(double), (size_t)p.N2 * sizeof(double), rows,
+                         cudaMemcpyDeviceToHost, im->stream));
+    CK(cudaStreamSynchronize(im->stream));
+}
+// Mass per column: a small per-step result for the end-to-end path to read back.
+__device__ inline void k_column_mass(const DevParams& p, double* out) {
+    __shared__ double red[32];
+    const int col = blockIdx.x;
+    double acc = 0;
+    for (int s = 0; s < p.S; s++)
+        for (int j = threadIdx.x; j < p.N2; j += blockDim.x) acc += p.u[idx_u(p, 0, col, s, j)] * p.vol[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (unsigned w = 0; w < (blockDim.x + 31) / 32; w++) t += red[w]; out[col] = t; }
+}
+struct MassArgs { DevParams p; double* out; };
+__global__ void k_column_mass_w(MassArgs a) { k_column_mass(a.p, a.out); }
+void Engine::column_mass(double* m) {
+    DevParams& p = im->p;
+    if (!im->d_mass) im->d_mass = im->dalloc<double>(p.ncol);
+    MassArgs a{p, im->d_mass};
+    AIO_LAUNCH(k_column_mass_w, p.ncol, 256, 0, im->stream, a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m, im->d_mass, (size_t)p.ncol * sizeof(double), cudaMemcpyDeviceToHost, im->stream));
+    CK(cudaStreamSynchronize(im->stream));
+}
+void Engine::sync() { CK(cudaStreamSynchronize(im->stream)); }
+
+}  // namespace aio
+
+#include "engine_more.inl"

@@ -12,7 +12,7 @@
 // through a virtual base pointer, eos.h:13-26): the first compute_primitive() of every step sees the
 // dt chosen for that step (advection.cpp:73-77 run before :152).
 //
-// usage: aiolos_ref_dump -dir <deckdir/> -par <file.par> [-spc <file.spc>] [-tmax T] -out <prefix>
+// usage: aiolos_ref_dump -dir <deckdir/> -par <file.par> [-spc <file.spc>] [-tmax T] [-nsteps K] -out <prefix>
 #include "aiolos.h"
 #include <cstdio>
 
@@ -30,15 +30,21 @@ template <typename M> static void putm(const std::string& name, const M& m) {
 }
 
 struct HookEOS final : public EOS_Base {
-    EOS_Base* inner; c_Sim* sim; std::vector<double>* dts; long long last = -1;
+    EOS_Base* inner; c_Sim* sim; std::vector<double>* dts; long long last = -1; long long stop_after = -1; int ncall = 0;
     HookEOS(EOS_Base* e, c_Sim* s, std::vector<double>* d) : inner(e), sim(s), dts(d) {}
     ~HookEOS() { delete inner; }
     void compute_primitive(const AOS* a, AOS_prim* b, int n) const override {
         HookEOS* self = const_cast<HookEOS*>(this);
-        if (sim->steps != self->last) {
-            self->last = sim->steps;
-            if (sim->steps >= 0 && (size_t)sim->steps >= dts->size()) dts->resize(sim->steps + 1, 0.0);
-            if (sim->steps >= 0) (*dts)[sim->steps] = sim->dt;
+        if (sim->steps != self->last) { self->last = sim->steps; self->ncall = 0; }
+        self->ncall++;
+        if (sim->steps >= 0) {
+            if ((size_t)sim->steps >= dts->size()) dts->resize(sim->steps + 1, 0.0);
+            (*dts)[sim->steps] = sim->dt;      // overwritten by every call of the step: the last one saw this step's dt
+            // -nsteps K: let step K-1 run with its natural dt, then leave the loop (its condition is globalTime < t_max,
+            // advection.cpp:60).  dt = min(dt, t_max - globalTime) (advection.cpp:75) must already have been evaluated:
+            // in step 0 the first call comes from the steps==0 priming (advection.cpp:67-71), before dt is chosen.
+            if (stop_after > 0 && sim->steps == stop_after - 1 && self->ncall >= (sim->steps == 0 ? 2 : 1))
+                sim->t_max = sim->globalTime;
         }
         inner->compute_primitive(a, b, n);
     }
@@ -113,6 +119,21 @@ static void dump_problem(c_Sim& s) {
     putv("photon_energies", s.photon_energies);
     { std::vector<double> t(s.BAND_IS_HIGHENERGY.begin(), s.BAND_IS_HIGHENERGY.end()); putv("BAND_IS_HIGHENERGY", t); }
     putm("solar_heating_final", s.solar_heating_final); putm("planck_matrix", s.planck_matrix);
+    {   // thermal (black-body) part of the top-of-atmosphere band fluxes, same expressions as init_and_bounds.cpp:808-826,
+        // so that a per-column PARI_UVSTAR / PARI_XSTAR override can be applied to a dump exactly as the constructor would
+        std::vector<double> th(s.num_bands_in, 0.0);
+        for (int b = 0; b < s.num_bands_in; b++) {
+            if (s.num_bands_in == 1) {
+                th[b]  = sigma_rad * pow(s.T_star,4.) * pow(s.R_star*rsolar,2.)/pow(s.planet_semimajor*au,2.);
+                th[b] += sigma_rad * pow(s.T_other,4.) * pow(s.R_other*rsolar,2.)/pow(s.d_other*au,2.);
+            } else {
+                th[b]  = sigma_rad * pow(s.T_star,4.) * pow(s.R_star*rsolar,2.)/pow(s.planet_semimajor*au,2.) * s.compute_planck_function_integral4(s.l_i_in[b], s.l_i_in[b+1], s.T_star);
+                th[b] += sigma_rad * pow(s.T_other,4.) * pow(s.R_other*rsolar,2.)/pow(s.d_other*au,2.) * s.compute_planck_function_integral4(s.l_i_in[b], s.l_i_in[b+1], s.T_other);
+            }
+        }
+        putv("solar_heating_thermal", th);
+        put1("fluxfile_used", s.fluxfile.compare("---") != 0 ? 1.0 : 0.0);
+    }
     putm("Jrad_init", s.Jrad_init); putm("highenergy_switch", s.highenergy_switch);
     putm("cell_optical_depth_highenergy", s.cell_optical_depth_highenergy);
     putm("friction_coeff_mask", s.friction_coeff_mask); putm("inv_totmasses", s.inv_totmasses);
@@ -149,7 +170,7 @@ static void dump_problem(c_Sim& s) {
 
 int main(int argc, char** argv) {
     std::string dir = "./", par = "", spc = "default.spc", out = "dump";
-    double tmax = -1; int have_tmax = 0;
+    double tmax = -1; int have_tmax = 0; long long nsteps = -1;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "-dir" && i + 1 < argc) dir = argv[++i];
@@ -157,6 +178,7 @@ int main(int argc, char** argv) {
         else if (a == "-spc" && i + 1 < argc) spc = argv[++i];
         else if (a == "-out" && i + 1 < argc) out = argv[++i];
         else if (a == "-tmax" && i + 1 < argc) { tmax = atof(argv[++i]); have_tmax = 1; }
+        else if (a == "-nsteps" && i + 1 < argc) { nsteps = atoll(argv[++i]); }
     }
     try {
         c_Sim sim(par, spc, dir, 0, 1, 99999999);
@@ -166,13 +188,16 @@ int main(int argc, char** argv) {
         dump_problem(sim);
         fclose(g_out);
         std::vector<double> dts;
-        sim.species[0].eos = new HookEOS(sim.species[0].eos, &sim, &dts);
+        HookEOS* hook = new HookEOS(sim.species[0].eos, &sim, &dts);
+        hook->stop_after = nsteps;
+        sim.species[0].eos = hook;
+        const double tmax_deck = sim.t_max;
         if (have_tmax) sim.t_max = tmax;
         sim.execute();
         g_out = fopen((out + "_final.bin").c_str(), "wb");
         if (!g_out) { perror("open"); return 2; }
         putv("dt_sequence", dts);
-        put1("t_max", sim.t_max);
+        put1("t_max", sim.t_max); put1("t_max_deck", tmax_deck);
         dump_state(sim);
         fclose(g_out);
     } catch (std::exception& e) {

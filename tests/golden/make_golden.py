@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference (oracle/_ref/aiolos_ref_dump,
+built by oracle/Makefile from /root/reference) on the reference's own decks.  Runs only in the dev container
+(/root/reference does not exist on the GPU box); the resulting *.bin files are committed.
+
+  <case>_init.bin     state right after the reference's constructor (input of aio_create_from_dump)
+  <case>_k<K>.bin     state after exactly K steps of c_Sim::execute() from t=0 (trimmed to the compared fields)
+
+usage: python tests/golden/make_golden.py [case ...]
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from aiodump import read_dump, write_dump  # noqa: E402
+
+RUN = "/tmp/aiolos_golden_run"
+DUMP = os.path.join(ROOT, "oracle", "_ref", "aiolos_ref_dump")
+
+# case -> (deck dir, par, spc or None, step counts)
+CASES = {
+    # BASELINE.json configs[0]: hydrostatic planet, 1 species, hydro only
+    "c1_planet_spherical": ("runs_searth/", "planet_spherical.par", "mix3.spc", [1, 100, 2000]),
+    # configs[1]: 6-species numeric friction (maintained twin of test2/cartesian_frictionMatrix6spc.par)
+    "c2_friction_6spc": ("test_files/", "friction_6spc.par", "friction_6spc.spc", [1, 100, 1000]),
+    # same deck made well-conditioned (T ~ 300 K, alpha*dt ~ 1): the shipped one starts at T ~ 1e-8 K where alpha*dt ~ 1e14
+    # and the reference's own LU result depends on FMA contraction (README.md in this directory)
+    "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc", [1, 100, 1000]),
+    # configs[2]: 22-band full FLD
+    "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc", [1, 20, 100]),
+    # configs[3]: hydro + 2-band irradiation + simple FLD
+    "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
+}
+
+KEEP_FINAL = ("dt_sequence", "t_max", "t_max_deck", "steps", "globalTime", "dt", "cflfactor", "timestep_rad2", "cfl_step",
+              "phi", "Jrad_FLD", "dS_band", "total_opacity", "T_planet")
+KEEP_SPECIES = ("u1", "u2", "u3", "temperature", "speed", "pres", "eint_last", "dS", "sound_speed", "phi_s")
+
+
+def run_case(name):
+    d, par, spc, steps = CASES[name]
+    subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), RUN], check=True, stdout=subprocess.DEVNULL)
+    for f in os.listdir(os.path.join(HERE, "decks")):        # our own deck variants live next to the reference's test decks
+        subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "test_files", f)], check=True)
+    for k in steps:
+        out = os.path.join(RUN, f"{name}_k{k}")
+        cmd = [DUMP, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]
+        if spc:
+            cmd += ["-spc", spc]
+        with open(out + ".log", "w") as log:
+            subprocess.run(cmd, cwd=RUN, stdin=subprocess.DEVNULL, stdout=log, stderr=subprocess.STDOUT, check=True)
+        fin = read_dump(out + "_final.bin")
+        assert int(fin["steps"][0]) == k, (name, k, fin["steps"])
+        keep = {key: v for key, v in fin.items()
+                if key in KEEP_FINAL or (key[0] == "s" and "." in key and key.split(".", 1)[1] in KEEP_SPECIES)}
+        write_dump(os.path.join(HERE, f"{name}_k{k}.bin"), keep)
+        if k == steps[0]:
+            init = read_dump(out + "_init.bin")
+            write_dump(os.path.join(HERE, f"{name}_init.bin"), init)
+        print(f"{name}: k={k} t={fin['globalTime'][0]:.6e} dt={fin['dt'][0]:.6e}")
+
+
+if __name__ == "__main__":
+    for c in (sys.argv[1:] or list(CASES)):
+        run_case(c)
