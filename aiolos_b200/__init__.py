@@ -45,6 +45,7 @@ _SYMBOLS = {
     "aio_advance": (C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]),
     "aio_run": (C.c_int, [C.c_void_p, C.c_double, C.c_longlong, C.POINTER(C.c_longlong)]),
     "aio_set_tmax": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "aio_kernel_times": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
     "aio_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "aio_status": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                              C.POINTER(C.c_int)]),
@@ -162,6 +163,12 @@ class Ensemble:
 
     def set_tmax(self, t_max: float, column: int = -1):
         self._ck(self._lib.aio_set_tmax(self._h, column, float(t_max)))
+
+    def kernel_times(self, steps: int):
+        """Average device ms per step of the hydro / friction / radiation kernels over ``steps`` ordinary steps."""
+        out = np.zeros(3)
+        self._ck(self._lib.aio_kernel_times(self._h, int(steps), out.ctypes.data))
+        return {"hydro": out[0], "friction": out[1], "radiation": out[2]}
 
     def set_option(self, key: str, value: str):
         self._ck(self._lib.aio_set_option(self._h, key.encode(), value.encode()))

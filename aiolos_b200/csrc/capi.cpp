@@ -152,6 +152,11 @@ int aio_run(aio_ensemble* e, double t_stop, long long max_steps, long long* step
     });
 }
 
+int aio_kernel_times(aio_ensemble* e, long long nsteps, double* ms3) {
+    if (!e || !ms3 || nsteps < 1) return fail(AIO_ERR_ARG, "aio_kernel_times: bad argument");
+    return guarded([&]() { e->eng->kernel_times(nsteps, ms3); return AIO_OK; });
+}
+
 int aio_set_tmax(aio_ensemble* e, int column, double t_max) {
     if (!e) return fail(AIO_ERR_ARG, "null handle");
     return guarded([&]() { e->eng->set_tmax(column, t_max); return AIO_OK; });

@@ -31,6 +31,7 @@ struct Engine::Impl {
     std::vector<ColState> h_cs;
     double* pinned = nullptr; size_t pinned_bytes = 0;
     double* d_mass = nullptr;
+    bool prof_on = false; cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr}; double prof_ms[3] = {0, 0, 0};
 
     template <typename T> T* dalloc(size_t n) {
         void* q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T))); allocs.push_back(q);
@@ -253,6 +254,7 @@ Engine::~Engine() {
     if (im->pinned) cudaFreeHost(im->pinned);
     if (im->ev0) cudaEventDestroy(im->ev0);
     if (im->ev1) cudaEventDestroy(im->ev1);
+    for (int k = 0; k < 4; k++) if (im->prof_ev[k]) cudaEventDestroy(im->prof_ev[k]);
     if (im->stream) cudaStreamDestroy(im->stream);
     delete im;
 }
@@ -268,6 +270,9 @@ void* Engine::stream() const { return (void*)im->stream; }
 void Engine::launch_step() {
     DevParams& p = im->p;
     const int ncol = p.ncol, NT = im->NT;
+    const bool prof = im->prof_on;
+    auto mark = [&](int k) { if (prof) CK(cudaEventRecord(im->prof_ev[k], im->stream)); };
+    mark(0);
     switch (im->CPT) {
     case 1: AIO_LAUNCH(k_hydro<1>, ncol, NT, im->smem_hydro, im->stream, p); break;
     case 2: AIO_LAUNCH(k_hydro<2>, ncol, NT, im->smem_hydro, im->stream, p); break;
@@ -275,7 +280,9 @@ void Engine::launch_step() {
     default: AIO_LAUNCH(k_hydro<8>, ncol, NT, im->smem_hydro, im->stream, p); break;
     }
     im->launches++;
+    mark(1);
     if (im->has_friction) { launch_friction(); im->launches++; }
+    mark(2);
     if (p.use_rad_fluxes == 2) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad_simple<1>, ncol, NT, im->smem_rad, im->stream, p); break;
@@ -285,6 +292,25 @@ void Engine::launch_step() {
         }
         im->launches++;
     } else if (p.use_rad_fluxes == 1) { launch_full(); im->launches++; }
+    mark(3);
+    if (prof) {
+        CK(cudaEventSynchronize(im->prof_ev[3]));
+        for (int k = 0; k < 3; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, im->prof_ev[k], im->prof_ev[k + 1])); im->prof_ms[k] += ms; }
+    }
+}
+
+// Per-kernel device time, measured live with CUDA events on the ensemble's stream: runs `nsteps` ordinary steps with an
+// event between the launches and returns the average milliseconds of {hydro, friction, radiation} per step.
+void Engine::kernel_times(long long nsteps, double* out3) {
+    if (!im->prof_ev[0]) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&im->prof_ev[k]));
+    for (int k = 0; k < 3; k++) im->prof_ms[k] = 0;
+    im->p.step_limit += nsteps;
+    im->prof_on = true;
+    for (long long k = 0; k < nsteps; k++) launch_step();
+    im->prof_on = false;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(im->stream));
+    for (int k = 0; k < 3; k++) out3[k] = nsteps > 0 ? im->prof_ms[k] / (double)nsteps : 0.0;
 }
 
 // Advance every column by up to `nsteps` further steps (columns that reach their t_max or crash stop earlier).

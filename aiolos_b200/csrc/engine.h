@@ -19,6 +19,7 @@ public:
     void clamp_tmax(double t_stop);                             // t_max = min(t_max, t_stop) for every column
     void column_mass(double* mass_per_column);                  // sum_s sum_j u1*vol, reduced on the device
     long long total_steps();
+    void kernel_times(long long nsteps, double* out3);          // avg device ms per step of {hydro, friction, radiation}
     void set_option(const std::string& key, const std::string& value);
     void status(int col, double* t, double* dt, long long* steps, int* state);
     void status_all(double* t, double* dt, long long* steps, int* state);

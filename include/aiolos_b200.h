@@ -73,6 +73,9 @@ int aio_advance(aio_ensemble* e, long long max_steps, double* device_ms);
 /* Run until every column reached min(t_max, t_stop) or crashed; returns the number of step launches in *steps_done. */
 int aio_run(aio_ensemble* e, double t_stop, long long max_steps, long long* steps_done);
 int aio_set_tmax(aio_ensemble* e, int column, double t_max);   /* column < 0: all */
+/* Advance nsteps steps with a CUDA event between the kernel launches; ms3 receives the average device milliseconds per
+ * step of the {hydro, friction, radiation} kernels (0 for a kernel the deck does not launch). */
+int aio_kernel_times(aio_ensemble* e, long long nsteps, double* ms3);
 
 /* Engine options.  "tridiag" = "pcr" (default: parallel cyclic reduction across the CTA) | "thomas" (validation mode:
  * the reference's elimination order, block_tridiag_solve.h:57-130, on one lane). */

@@ -1,0 +1,105 @@
+"""Parity tests proper: the CUDA path (libaiolos_b200.so, through the C ABI) against the oracle's golden output, plus
+size-independent properties at the full ensemble size of BASELINE.json (4096 columns)."""
+import os
+
+import numpy as np
+import pytest
+
+import aiolos_b200 as A
+from parity import GOLDEN, compare_with_golden, run_case
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("c1_planet_spherical", 1, 1e-10), ("c1_planet_spherical", 100, 1e-8), ("c1_planet_spherical", 2000, 1e-8),
+    ("c2m_friction_6spc_mild", 1, 1e-10), ("c2m_friction_6spc_mild", 100, 1e-8), ("c2m_friction_6spc_mild", 1000, 1e-8),
+    ("c4_dynamic3_euv", 1, 1e-10), ("c4_dynamic3_euv", 100, 1e-8),
+]
+
+
+@pytest.fixture(scope="module")
+def lib(product_lib):
+    L = A.load_library(product_lib)
+    assert L.aio_device_count() > 0, "no CUDA device visible"
+    assert b"sm_100a" in L.aio_version()
+    return product_lib
+
+
+@pytest.mark.parametrize("case,k,tol", CASES)
+def test_fields_match_reference(lib, case, k, tol):
+    ens, ref = run_case(A, lib, case, k)
+    st = ens.status(0)
+    assert st["steps"] == k and st["state"] == 0
+    assert abs(st["t"] - ref["globalTime"][0]) <= 1e-9 * ref["globalTime"][0]
+    errs = compare_with_golden(ens, ref)
+    bad = {f: e for f, e in errs.items() if not e <= tol}
+    assert not bad, f"{case} k={k}: {bad}"
+    assert ens.kernel_launches >= k
+
+
+def test_c4_cfl_regime(lib):
+    for opt, tol in (("thomas", 1e-9), ("pcr", 1e-7)):
+        ens, ref = run_case(A, lib, "c4_dynamic3_euv", 1000, options={"tridiag": opt})
+        errs = compare_with_golden(ens, ref)
+        assert max(errs[f] for f in ("s0.u1", "s0.u2", "s0.u3")) < tol, (opt, errs)
+
+
+@pytest.mark.parametrize("case,k", [("c1_planet_spherical", 300), ("c4_dynamic3_euv", 300), ("c2m_friction_6spc_mild", 300)])
+def test_dt_sequence(lib, case, k):
+    from aiodump import read_dump
+    kk = max(int(f.split("_k")[1][:-4]) for f in os.listdir(GOLDEN) if f.startswith(case + "_k"))
+    ens = A.Ensemble.from_dump(os.path.join(GOLDEN, f"{case}_init.bin"), ncols=1, lib=lib)
+    dts = read_dump(os.path.join(GOLDEN, f"{case}_k{kk}.bin"))["dt_sequence"]
+    for i in range(k):
+        ens.advance(1)
+        st = ens.status(0)
+        assert st["steps"] == i + 1
+        assert abs(st["dt"] - dts[i]) <= 1e-12 * dts[i], (i, st["dt"], dts[i])
+
+
+def test_shipped_friction_deck(lib):
+    ens, ref = run_case(A, lib, "c2_friction_6spc", 1)
+    v = [ens.get("speed", 0, s)[5] for s in range(ens.num_species)]
+    assert np.ptp(v) < 1e-9 * abs(np.mean(v))
+    assert abs(np.mean(v) - ref["s0.speed"][5]) < 5e-2 * abs(ref["s0.speed"][5])
+    for s in range(ens.num_species):
+        assert np.array_equal(ens.get("u1", 0, s), ref[f"s{s}.u1"])
+
+
+def test_full_ensemble_properties(lib):
+    """4096 columns of configs[3] (BASELINE's full size): identical columns stay bit-identical, the deck-valued column
+    reproduces the golden run, heating is monotone in the EUV flux, and the state round-trips through host buffers."""
+    n = 4096
+    uv = [1e31 * 10 ** (-2 + 4 * k / (n - 1)) for k in range(n)]
+    ov = [(k, "PARI_UVSTAR", repr(uv[k])) for k in range(2, n)]          # columns 0 and 1 keep the deck value 1e31
+    ens = A.Ensemble.from_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_init.bin"), ncols=n, overrides=ov, lib=lib)
+    ens.advance(100)
+    st = ens.status_all()
+    assert (st["steps"] == 100).all() and (st["state"] == 0).all()
+    from aiodump import read_dump
+    ref = read_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_k100.bin"))
+    assert max(compare_with_golden(ens, ref, column=0).values()) < 1e-8
+    for f in ("u1", "u2", "u3", "J", "dS"):
+        assert np.array_equal(ens.get(f, 0), ens.get(f, 1))
+    # stellar heating of the outermost cells grows with the column's EUV flux
+    ds = np.array([ens.get("dS", c)[ens.num_cells - 5] for c in range(2, n, 97)])
+    assert (np.diff(ds) > 0).all()
+    u = ens.download_state()
+    assert u.shape == (3, n, 1, ens.num_cells + 2)
+    assert np.array_equal(u[0, 0, 0], ens.get("u1", 0))
+    ens.upload_state(u)
+    assert np.array_equal(ens.download_state(), u)
+    m = ens.column_mass()
+    assert m.shape == (n,) and np.isfinite(m).all() and abs(m[0] - m[1]) == 0
+
+
+def test_crashed_column_freezes_others_continue(lib):
+    """A column pushed to a negative temperature stops (soft crash, advection.cpp:282-307); its neighbours keep stepping."""
+    ens = A.Ensemble.from_dump(os.path.join(GOLDEN, "c1_planet_spherical_init.bin"), ncols=3, lib=lib)
+    u = ens.download_state()
+    u[2, 1, 0, 10] = -abs(u[2, 1, 0, 10])          # negative total energy in one cell of column 1
+    ens.upload_state(u)
+    ens.advance(5)
+    st = ens.status_all()
+    assert st["state"][1] == 1 and st["steps"][1] == 1
+    assert st["state"][0] == 0 and st["steps"][0] == 5 and st["steps"][2] == 5
