@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""Turn an .ncu-rep (ncu --set full) into the short text summary committed under profiles/.
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("=" * 100)
+        print("kernel:", r[hdr.index("Kernel Name")], " grid", r[hdr.index("Grid Size")], " block", r[hdr.index("Block Size")])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:75s} {r[i]:>18s} {units[i]}")
+        stalls = []
+        for i, h in enumerate(hdr):
+            if "smsp__average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
+                try:
+                    stalls.append((float(r[i]), h.split("stalled_")[1].split("_per_issue")[0]))
+                except ValueError:
+                    pass
+        stalls.sort(reverse=True)
+        print("  warp stall reasons (warps per issue-active cycle):", ", ".join(f"{n} {v:.2f}" for v, n in stalls[:8]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
