@@ -89,6 +89,7 @@ struct DevParams {
     // per-column state
     double *u, *eint, *phi, *phis, *J, *dS;
     double *dSband_top;                 // [ncol][Bin] dS_band(N,b) of the previous step (radiation.cpp:263-265)
+    double *Xstore;                     // full FLD: [ncol][N2][n][Bout+1]  X_i = S_i^-1 u_i and S_i^-1 rhs_i (rad_full.cuh)
     double *Tsave, *cssave;             // [ncol][S][NP] prim.temperature / prim.sound_speed as left by the post-hydro
                                         // compute_pressure: friction changes u but not these (source.cpp:485-505), and the
                                         // radiation solvers and the next CFL estimate read the stale values

@@ -86,6 +86,7 @@ static void check_supported(const Problem& q) {
     if (q.use_rad_fluxes < 0 || q.use_rad_fluxes > 2) fail("PARI_USE_RADIATION outside 0..2");
     if (q.use_rad_fluxes == 2 && q.num_bands_out != 1) fail("simple FLD solver needs NUM_BANDS_OUT 1");
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating) fail("simple FLD + collisional heating with >1 species");
+    if (q.use_rad_fluxes == 1 && q.num_species > 1 && q.use_collisional_heating) fail("full FLD + collisional heating with >1 species");
     if (q.use_rad_fluxes && q.opacity_model != 'C' && q.opacity_model != 'P') fail(std::string("opacity model ") + q.opacity_model);
     if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
     if (q.use_avg_temperature) fail("USE_AVG_T 1");

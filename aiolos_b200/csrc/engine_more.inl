@@ -13,7 +13,35 @@ void Engine::launch_friction() {
     else throw std::runtime_error("unsupported configuration: more than 8 species with friction");
 }
 
-void Engine::full_setup() {}
-void Engine::launch_full() { throw std::runtime_error("unsupported configuration: PARI_USE_RADIATION 1 kernel not built yet"); }
+// Full FLD (PARI_USE_RADIATION 1): one warp per column, two columns per CTA (rad_full.cuh).
+void Engine::full_setup() {
+    DevParams& p = im->p;
+    p.Xstore = nullptr;
+    if (p.use_rad_fluxes != 1) return;
+    const FullDims fd = full_dims(p.Bout, p.S, p.Bin);
+    if (fd.n > 32 || p.Bin > 32) throw std::runtime_error("unsupported configuration: full FLD with more than 32 unknowns per cell");
+    const size_t words = (size_t)p.ncol * p.N2 * fd.n * (p.Bout + 1);
+    size_t free_b = 0, total_b = 0;
+#ifndef AIO_EMU_BUILD
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (words * sizeof(double) > free_b * 9 / 10)
+        throw std::runtime_error("unsupported configuration: full FLD factor storage does not fit in HBM; use fewer columns per GPU");
+#endif
+    p.Xstore = im->dalloc<double>(words);
+    im->nt_full = 64;
+    im->smem_full = (size_t)(im->nt_full / 32) * fd.per_warp * sizeof(double);
+    int maxsm = 0; int dev = 0;
+#ifndef AIO_EMU_BUILD
+    CK(cudaGetDevice(&dev));
+#endif
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (im->smem_full > (size_t)maxsm) throw std::runtime_error("unsupported configuration: full FLD block does not fit in shared memory");
+    CK(cudaFuncSetAttribute(k_rad_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+}
+void Engine::launch_full() {
+    DevParams& p = im->p;
+    const int wpb = im->nt_full / 32;
+    AIO_LAUNCH(k_rad_full, (p.ncol + wpb - 1) / wpb, im->nt_full, im->smem_full, im->stream, p);
+}
 
 }  // namespace aio

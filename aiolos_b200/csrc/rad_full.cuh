@@ -1,5 +1,350 @@
-// Full FLD solver (PARI_USE_RADIATION 1): coupled J_b / T_s block-tridiagonal system.  See rad_full kernels below.
+// Full FLD solver (PARI_USE_RADIATION 1): coupled J_b / T_s system, one WARP per column.
+//   update_opacities (models C/P)      reference opacities.cpp:74-369
+//   reset_dS / update_dS               radiation.cpp:15-348     lane = incoming band, sequential top-down optical depth
+//   update_fluxes_FLD                  radiation.cpp:353-840    assembly of the block-tridiagonal system, n = Bout + S
+//   BlockTriDiagSolver                 block_tridiag_solve.h:57-130   block Thomas, PartialPivLU per block
+//   compute_planck_function_integral3  helpers.cpp:227-300
+//
+// Layout of the work: the off-diagonal blocks l_i, u_i only carry the diagonal of their J-J part (radiation.cpp:431-434),
+// so  S_i = d_i - l_i S_{i-1}^{-1} u_{i-1}  needs  X_{i-1} = S_{i-1}^{-1} u_{i-1}  (n x Bout) and touches only J rows.
+// Per cell the warp keeps the augmented matrix [S_i | u_i | rhs_i] in a warp-private shared-memory tile (lane = row during
+// the elimination, lane = right-hand-side column during the back substitution; odd leading dimension => no bank
+// conflicts either way) and runs the LU exactly as Eigen's PartialPivLU does (first-max pivot with physical row swaps,
+// zero pivot => no scaling, back substitution skips exactly-zero unknowns -- the all-zero T rows of the last ghost cell
+// rely on that).  X_i and S_i^{-1} rhs_i are written to HBM (n*(Bout+1) doubles per cell) for the back sweep
+//   x_i = A_i - X_i x_{i+1}.
 #pragma once
 #include "common.cuh"
+#include "hydro.cuh"
+#include "rad_simple.cuh"
+
 namespace aio {
+
+// helpers.cpp:227-300
+__device__ inline double planck_integral3(const DevParams& p, double lmin, double lmax, double temperature) {
+    if (p.Bout == 1) return 1;
+    const double* P = p.planck_matrix;             // [num_plancks][2]: lambda*T, cumulative power
+    double lT_min, lT_max;
+    if (temperature < 2.71) { lT_min = lmin * 2.71; lT_max = lmax * 2.71; }
+    else { lT_min = lmin * temperature; lT_max = lmax * temperature; }
+    double m, power_min, power_max;
+    const int np = p.num_plancks;
+    if (lT_min < P[0]) {
+        m = P[1] / P[0];
+        power_min = P[1] + m * lT_min;
+        if (lT_max < P[0]) return 1.;
+    } else {
+        const int imin = (int)(log(lT_min / P[0]) / log(p.lT_spacing));
+        m = (P[2 * (imin + 1) + 1] - P[2 * imin + 1]) / (P[2 * (imin + 1)] - P[2 * imin]);
+        power_min = P[2 * imin + 1] + m * (lT_min - P[2 * imin]);
+    }
+    if (lmax * temperature > P[2 * (np - 1)]) {
+        power_max = 1.;
+        if (lT_min > P[2 * (np - 1)]) return 1;
+    } else {
+        const int imax = (int)(log(lT_max / P[0]) / log(p.lT_spacing));
+        m = (P[2 * (imax + 1) + 1] - P[2 * imax + 1]) / (P[2 * (imax + 1)] - P[2 * imax]);
+        power_max = P[2 * imax + 1] + m * (lT_max - P[2 * imax]);
+    }
+    return power_max - power_min;
+}
+
+struct FullDims { int n, LD, LDX, per_warp; };
+__host__ __device__ inline FullDims full_dims(int Bout, int S, int Bin) {
+    FullDims d;
+    d.n = Bout + S;
+    d.LD = d.n + Bout + 1; if ((d.LD & 1) == 0) d.LD++;      // augmented row: S | u columns | rhs ; odd => conflict-free
+    d.LDX = Bout + 1; if ((d.LDX & 1) == 0) d.LDX++;
+    // tile, previous X (+A), x of the cell above, fac[S][Bout], contributions[S][Bin], scratch
+    d.per_warp = d.n * d.LD + d.n * d.LDX + d.n + S * Bout + S * Bin + 2 * S + 8;
+    return d;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_or(int v) {
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
+    AIO_DYN_SMEM(double, sm);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int col = blockIdx.x * wpb + wib;
+    if (col >= p.ncol) return;
+    ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const double dt = cst.dt, tnow = cst.t;
+    const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin, Bout = p.Bout;
+    const FullDims fd = full_dims(Bout, S, Bin);
+    const int n = fd.n, LD = fd.LD, LDX = fd.LDX, NA = n + Bout + 1;      // NA = used columns of the augmented tile
+    double* A = sm + (size_t)wib * fd.per_warp;      // [n][LD]
+    double* Xp = A + n * LD;                         // [n][LDX]: X_{i-1} (Bout columns) and A_{i-1} (column Bout)
+    double* xs = Xp + n * LDX;                       // [n]
+    double* facs = xs + n;                           // [S][Bout]
+    double* contrib = facs + S * Bout;               // [S][Bin]
+    double* misc = contrib + S * Bin;                // [2S + 8]
+    const int KA = Bin + 2 * Bout;
+    const double* kap = p.kappa_avg;
+    double* Xg = p.Xstore + (size_t)col * N2 * n * (Bout + 1);
+
+    // ---- stellar heating: lane = incoming band, top-down exactly as radiation.cpp:51-63,154-348 ----------------------------
+    {
+        const int b = lane;
+        double F = 0, rad_above = 0, top_prev = 0;
+        if (b < Bin) {
+            F = p.solar_heating_final[(size_t)col * Bin + b];
+            if (tnow < p.radiation_rampup_time)
+                F = F * (p.init_radiation_factor + (1. - p.init_radiation_factor) * tnow / p.radiation_rampup_time);
+            top_prev = p.dSband_top[(size_t)col * Bin + b];
+        }
+        for (int j = N + 1; j > 0; j--) {
+            const double dxj = __ldg(p.dx + j);
+            if (b < Bin) {
+                double tot = 0;
+                for (int s = 0; s < S; s++) tot += kap[s * KA + b] * p.u[idx_u(p, 0, col, s, j)];
+                const double cell_tau = tot * dxj;
+                const double rad_j = (j == N + 1) ? 0. : rad_above + cell_tau;
+                double dSb;
+                if (j < N + 1) {
+                    const double Sb = F * exp(-rad_above);
+                    dSb = 0.25 * Sb / dxj * (1. - p.bond_albedo);
+                    const double dtau_tot = -(rad_above - rad_j);
+                    double dS_he = dSb;
+                    if (dtau_tot > 1e-3) dSb *= (-expm1(-dtau_tot));
+                    else dSb *= (-fastexpm1_2(-dtau_tot));
+                    dS_he *= -fastexpm1_2(-0.);
+                    dSb -= dS_he;
+                    dSb = smax(dSb, 0.);
+                } else {
+                    dSb = top_prev;
+                }
+                if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
+                for (int s = 0; s < S; s++) {
+                    const double hsw = p.highenergy_switch[s * Bin + b];
+                    const double frac = hsw * kap[s * KA + b] * p.u[idx_u(p, 0, col, s, j)] * dxj / cell_tau;
+                    contrib[s * Bin + b] = hsw * dSb * frac;
+                }
+                rad_above = rad_j;
+            }
+            __syncwarp();
+            if (lane < S) {
+                double acc = 0.;                              // reset_dS
+                for (int bb = 0; bb < Bin; bb++) { acc += contrib[lane * Bin + bb]; if (acc < 1e-50) acc = 0.; }
+                p.dS[idx_s(p, col, lane, j)] = acc;
+            }
+            __syncwarp();
+        }
+        if (lane < S) p.dS[idx_s(p, col, lane, 0)] = 0.;
+    }
+
+    // ---- forward sweep over cells: assemble block row i, S_i, LU, X_i = S_i^{-1} u_i, A_i = S_i^{-1}(r_i - l_i A_{i-1}) --------
+    const bool isJ = lane < Bout, isT = (lane >= Bout && lane < n);
+    const int sT = lane - Bout;
+    double D_prev = 0;                  // D_{i-1,b} of the J row this lane owns
+    double to_i = 0, to_ip = 0;         // total_opacity(i,b), total_opacity(i+1,b)
+    auto total_opacity = [&](int j, int b) -> double {
+        if (j < 1 || j > N + 1) return 0.;
+        double tot = 0;
+        for (int s = 0; s < S; s++) tot = fmax(kap[s * KA + Bin + Bout + b] * p.u[idx_u(p, 0, col, s, j)], tot);
+        return tot;
+    };
+    if (isJ) to_ip = total_opacity(0, lane);
+    double Jcur = 0, Jnext = isJ ? p.J[idx_J(p, col, lane, 0)] : 0.;
+    for (int i = 0; i < N2; i++) {
+        // zero the tile
+        for (int k = lane; k < n * LD; k += 32) A[k] = 0.;
+        __syncwarp();
+        // fac[s][b] = no_rad_trans * kappa_P * sigma T^3 / pi * planck fraction   (lane b, all species)
+        if (isJ && i <= N) {
+            for (int s = 0; s < S; s++) {
+                const SpeciesConst sc = p.sp[s];
+                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                facs[s * Bout + lane] = 1. * p.no_rad_trans * kap[s * KA + Bin + lane] * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
+                                        planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts);
+            }
+        }
+        __syncwarp();
+        double l_rr = 0, u_rr = 0, rhs = 0;
+        if (isJ) {
+            const int b = lane;
+            Jcur = Jnext;
+            Jnext = (i + 1 < N2) ? p.J[idx_J(p, col, b, i + 1)] : 0.;
+            to_i = to_ip;
+            to_ip = total_opacity(i + 1, b);
+            double d = 0;
+            if (i >= 2 && i <= N + 1) { d = D_prev; l_rr = -D_prev; }
+            if (i <= N) {
+                const double tv = __ldg(p.vol + i) / (C_CLIGHT * dt);
+                d += tv;
+                rhs += tv * Jcur;
+            }
+            double D_i = 0;
+            if (i >= 1 && i <= N) {
+                const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+                const double rhokr = sqrt(to_i * to_ip);
+                const double tau_inv = 1. / (dxc * rhokr);
+                const double R = p.xi_rad * tau_inv * fabs(Jnext - Jcur) / (Jcur + 1e-300);
+                D_i = 1. * tau_inv * 1. * __ldg(p.surf + i) * flux_limiter(R);
+                u_rr = -D_i; d += D_i;
+            }
+            D_prev = D_i;
+            if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
+            if (p.closed_radiative_boundaries) {
+                if (i >= N2 - p.ng) { l_rr = -d; u_rr = 0; rhs = 0; }
+            } else if (i == N + 1) {
+                double f = __ldg(p.x_i12 + N) / __ldg(p.x_i12 + N + 1);
+                if (p.geometry == 0) f = 1;
+                else if (p.geometry == 2) f *= f;
+                l_rr = -f * d; u_rr = 0; rhs = 0;
+            }
+            if (i <= N && !(i < p.ng || i >= N + 2 - p.ng)) {
+                const double vj = __ldg(p.vol + i);
+                for (int s = 0; s < S; s++) {
+                    const SpeciesConst sc = p.sp[s];
+                    const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                    Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                    const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                    const double fac = facs[s * Bout + b];
+                    d += vj * q.rho * kap[s * KA + Bin + b] * p.no_rad_trans;
+                    A[b * LD + Bout + s] = -4 * vj * q.rho * fac;
+                    rhs -= 3 * vj * q.rho * fac * Ts;
+                }
+            }
+            A[b * LD + b] = d;
+        } else if (isT && i <= N) {
+            const int s = sT;
+            const SpeciesConst sc = p.sp[s];
+            const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+            Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+            const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+            double d = 1 / dt;
+            rhs = Ts / dt;
+            rhs += (p.dS[idx_s(p, col, s, i)] + 0.) / u1 / sc.cv;
+            for (int b = 0; b < Bout; b++) {
+                const double fac = facs[s * Bout + b];
+                d += 16 * C_PI * fac / sc.cv;
+                A[lane * LD + b] = -4 * C_PI * kap[s * KA + Bin + b] * p.no_rad_trans / sc.cv;
+                rhs += 12 * C_PI * fac * Ts / sc.cv;
+            }
+            A[lane * LD + lane] = d;
+        }
+        // S_i = d_i - l_i X_{i-1} ;  rhs_i - l_i A_{i-1}   (only J rows have l entries)
+        if (isJ && i > 0 && l_rr != 0.) {
+            for (int c = 0; c < Bout; c++) A[lane * LD + c] -= l_rr * Xp[lane * LDX + c];
+            rhs -= l_rr * Xp[lane * LDX + Bout];
+        }
+        if (lane < n) {
+            if (isJ) A[lane * LD + n + lane] = u_rr;
+            A[lane * LD + n + Bout] = rhs;
+        }
+        __syncwarp();
+
+        // ---- PartialPivLU of the n x n block, the right-hand-side columns ride along ----------------------------------------
+        for (int k = 0; k < n; k++) {
+            double v = (lane >= k && lane < n) ? fabs(A[lane * LD + k]) : -1.;
+            const double big = warp_max(v);
+            // first row (smallest index) holding the maximum
+            unsigned m = __ballot_sync(0xffffffffu, v == big);
+            const int piv = __ffs(m) - 1;
+            if (big != 0.0) {
+                if (piv != k) {
+                    for (int c = lane; c < NA; c += 32) { const double t = A[k * LD + c]; A[k * LD + c] = A[piv * LD + c]; A[piv * LD + c] = t; }
+                    __syncwarp();
+                }
+                if (lane > k && lane < n) A[lane * LD + k] /= A[k * LD + k];
+            }
+            if (lane > k && lane < n) {
+                const double l = A[lane * LD + k];
+                if (l != 0.) {
+                    for (int c = k + 1; c < n; c++) A[lane * LD + c] = d_fnma(l, A[k * LD + c], A[lane * LD + c]);
+                    for (int c = n; c < NA; c++) {
+                        const double z = A[k * LD + c];
+                        if (z != 0.) A[lane * LD + c] = d_fnma(l, z, A[lane * LD + c]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- back substitution, lane = right-hand-side column (Bout columns of u_i and the rhs) ---------------------------------
+        if (lane < Bout + 1) {
+            const int c = n + lane;
+            for (int k = n - 1; k >= 0; k--) {
+                double z = A[k * LD + c];
+                if (z != 0.) {
+                    z /= A[k * LD + k];
+                    A[k * LD + c] = z;
+                    for (int r = 0; r < k; r++) A[r * LD + c] = d_fnma(z, A[r * LD + k], A[r * LD + c]);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- keep X_i / A_i for the next cell and for the back sweep -------------------------------------------------------------
+        double* Xi = Xg + (size_t)i * n * (Bout + 1);
+        for (int k = lane; k < n * (Bout + 1); k += 32) {
+            const int r = k / (Bout + 1), c = k - r * (Bout + 1);
+            const double v = A[r * LD + n + c];
+            Xp[r * LDX + c] = v;
+            Xi[k] = v;
+        }
+        __syncwarp();
+    }
+
+    // ---- back sweep  x_i = A_i - X_i x_{i+1},  store J, clamp T, e <- T, p <- e, cons <- prim, step tail ---------------------------
+    TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
+    int negJ = 0; double negJval = 0;
+    for (int i = N2 - 1; i >= 0; i--) {
+        const double* Xi = Xg + (size_t)i * n * (Bout + 1);
+        double x = 0;
+        if (lane < n) {
+            x = Xi[lane * (Bout + 1) + Bout];
+            if (i < N2 - 1) {
+                double t = 0;
+                for (int c = 0; c < Bout; c++) t += Xi[lane * (Bout + 1) + c] * xs[c];
+                x = x - t;
+            }
+        }
+        __syncwarp();
+        if (lane < n) xs[lane] = x;
+        __syncwarp();
+        if (isJ) {
+            double Jv = x;
+            if (p.couple_J_into_T && i <= N - 1 && Jv < 0) {           // advection.cpp:308-338
+                if (Jv > -1e-10) Jv *= -1.;
+                else { negJ = 1; negJval = Jv; }
+            }
+            p.J[idx_J(p, col, lane, i)] = Jv;
+        } else if (isT) {
+            const int s = sT;
+            const SpeciesConst sc = p.sp[s];
+            double T = x;
+            if (T < p.temperature_floor) T = p.temperature_floor;
+            if (T > p.max_temperature) T = p.max_temperature;
+            const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+            Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+            const double e_old = eint_of(q.p, q.rho, sc.gm1);
+            const double cs_old = p.cssave ? p.cssave[idx_s(p, col, s, i)] : cs_of(e_old, sc.gm1);
+            const double e = T * sc.cv;
+            q.p = e * q.rho * sc.gm1;
+            double n1, n2, n3;
+            prim_to_cons(q, sc.gm1, n1, n2, n3);
+            p.u[idx_u(p, 0, col, s, i)] = n1; p.u[idx_u(p, 1, col, s, i)] = n2; p.u[idx_u(p, 2, col, s, i)] = n3;
+            tail_cell(p, col, s, i, q.v, cs_old, e, T, acc);
+        }
+    }
+    const double ms = warp_max(acc.minstep), md = warp_max(acc.maxde);
+    const int bad = warp_or(acc.bad), nj = warp_or(negJ);
+    const double njv = -warp_max(negJ ? -negJval : -1e308);
+    if (lane == 0) {
+        cst.minstep = ms; cst.maxde = md;
+        cst.steps += 1;
+        if (bad) { cst.status = COL_NEG_T; cst.t = 1.1 * cst.t_max; }
+        else if (nj) { cst.status = COL_NEG_J; cst.crash_value = njv; cst.t = 1.1 * cst.t_max; }
+    }
+}
+
 }  // namespace aio

@@ -87,6 +87,13 @@ inline int __shfl_sync(unsigned, int v, int lane) {
     const unsigned src = (t & ~31u) | ((unsigned)lane & 31u);
     int r = (src < blockDim.x) ? emu::xi[src] : v; emu::sync_warp(); return r;
 }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned t = threadIdx.x; emu::xi[t] = pred ? 1 : 0; emu::sync_warp();
+    unsigned m = 0; const unsigned base = t & ~31u;
+    for (unsigned k = 0; k < 32 && base + k < blockDim.x; k++) if (emu::xi[base + k]) m |= (1u << k);
+    emu::sync_warp(); return m;
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ffs((int)v) : 0; }
 inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dsqrt_rn(double x) { return std::sqrt(x); }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }

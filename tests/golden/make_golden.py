@@ -30,7 +30,7 @@ CASES = {
     # and the reference's own LU result depends on FMA contraction (README.md in this directory)
     "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc", [1, 100, 1000]),
     # configs[2]: 22-band full FLD
-    "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc", [1, 20, 100]),
+    "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc", [1, 20, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
 }

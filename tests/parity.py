@@ -26,7 +26,9 @@ def compare_with_golden(ens, ref, column=0, fields=("u1", "u2", "u3")):
         cs = ref[f"s{s}.sound_speed"]
         out[f"s{s}.u1"] = rel_err(u1, r1)
         out[f"s{s}.u2"] = rel_err(u2, r2, np.abs(r1 * cs))
-        out[f"s{s}.u3"] = rel_err(u3, r3)
+        # energy scale: where the full FLD solver leaves T = 0 in the last ghost cell (singular block) E is pure
+        # kinetic round-off noise, so rho*c_s^2 of the pre-radiation state bounds the scale from below
+        out[f"s{s}.u3"] = rel_err(u3, r3, np.maximum(np.abs(r3), np.abs(r1 * cs * cs)))
     if ens.num_bands_out and "Jrad_FLD" in ref and ref["Jrad_FLD"].size == (ens.num_cells + 2) * ens.num_bands_out:
         J = ref["Jrad_FLD"].reshape(ens.num_cells + 2, ens.num_bands_out)
         for b in range(ens.num_bands_out):

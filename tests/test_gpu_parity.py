@@ -14,6 +14,7 @@ CASES = [
     ("c1_planet_spherical", 1, 1e-10), ("c1_planet_spherical", 100, 1e-8), ("c1_planet_spherical", 2000, 1e-8),
     ("c2m_friction_6spc_mild", 1, 1e-10), ("c2m_friction_6spc_mild", 100, 1e-8), ("c2m_friction_6spc_mild", 1000, 1e-8),
     ("c4_dynamic3_euv", 1, 1e-10), ("c4_dynamic3_euv", 100, 1e-8),
+    ("c3_searth_22b", 1, 1e-10), ("c3_searth_22b", 100, 1e-8), ("c3_searth_22b", 1000, 1e-8),
 ]
 
 
