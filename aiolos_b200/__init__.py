@@ -51,6 +51,7 @@ _SYMBOLS = {
                              C.POINTER(C.c_int)]),
     "aio_status_all": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aio_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "aio_problem_field": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]),
     "aio_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aio_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aio_column_mass": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -191,6 +192,15 @@ class Ensemble:
             fid += band
         out = np.empty(self.num_cells + 2)
         self._ck(self._lib.aio_get(self._h, column, species, fid, out.ctypes.data, out.size))
+        return out
+
+    def problem_field(self, name: str, column: int = 0) -> np.ndarray:
+        """An array/scalar the front end built for this column, by the reference's member name."""
+        n = self._lib.aio_problem_field(self._h, column, name.encode(), None, 0)
+        if n < 0:
+            raise AiolosError(n, self._lib.aio_last_error().decode())
+        out = np.empty(n)
+        self._lib.aio_problem_field(self._h, column, name.encode(), out.ctypes.data, n)
         return out
 
     def upload_state(self, u: np.ndarray):

@@ -182,6 +182,14 @@ int aio_get(aio_ensemble* e, int column, int species, int field, double* dst, in
     return guarded([&]() { e->eng->get_field(column, species, field, dst, n); return AIO_OK; });
 }
 
+int aio_problem_field(aio_ensemble* e, int column, const char* name, double* dst, int capacity) {
+    if (!e || !name || column < 0 || column >= (int)e->problems.size() || capacity < 0) { fail(AIO_ERR_ARG, "aio_problem_field: bad argument"); return AIO_ERR_ARG; }
+    std::vector<double> v;
+    if (!aio::problem_field(e->problems[column], name, v)) return fail(AIO_ERR_ARG, std::string("aio_problem_field: unknown field ") + name);
+    if (dst) for (int k = 0; k < capacity && k < (int)v.size(); k++) dst[k] = v[k];
+    return (int)v.size();
+}
+
 int aio_upload_state(aio_ensemble* e, const double* u) {
     if (!e || !u) return fail(AIO_ERR_ARG, "aio_upload_state: bad argument");
     return guarded([&]() { e->eng->upload_u(u); return AIO_OK; });

@@ -97,4 +97,44 @@ bool problem_from_dump(const DumpMap& d, Problem& p, std::string& err) {
     return g.ok;
 }
 
+// Named access to a Problem's arrays and scalars (same names as the oracle dump records): lets the tests compare what the
+// front end built from the input files with what the reference's constructor built.
+bool problem_field(const Problem& p, const std::string& name, std::vector<double>& out) {
+#define V(x) if (name == #x) { out = p.x; return true; }
+#define D(x) if (name == #x) { out.assign(1, (double)p.x); return true; }
+    V(x_i) V(x_i12) V(x_iVC) V(dx) V(surf) V(vol) V(omegaplus) V(omegaminus) V(source_pressure_prefactor_left)
+    V(source_pressure_prefactor_right) V(phi) V(K_zz) V(l_i_in) V(l_i_out) V(photon_energies) V(solar_heating)
+    V(solar_heating_final) V(solar_heating_thermal) V(planck_matrix) V(Jrad_FLD) V(Jrad_init) V(highenergy_switch) V(dS_band)
+    V(friction_coeff_mask) V(inv_totmasses) V(resonant_pair_matrix)
+    D(num_cells) D(num_species) D(num_bands_in) D(num_bands_out) D(num_ghosts) D(order) D(geometry) D(problem_number)
+    D(use_rad_fluxes) D(use_tides) D(friction_solver) D(photochemistry_level) D(use_collisional_heating) D(dt) D(cflfactor)
+    D(t_max) D(max_timestep_change) D(dt_min_init) D(timestep_rad2) D(energy_epsilon) D(CFL_break_time) D(planet_mass)
+    D(star_mass) D(init_star_mass) D(planet_semimajor) D(rs) D(domain_min) D(domain_max) D(alpha_collision) D(alpha_collision_ions)
+    D(bond_albedo) D(xi_rad) D(no_rad_trans) D(temperature_floor) D(max_temperature) D(const_opacity_solar_factor)
+    D(const_opacity_rosseland_factor) D(const_opacity_planck_factor) D(T_star) D(UV_star) D(R_star) D(lT_spacing) D(init_wind)
+    D(collision_model) D(opacity_model) D(closed_radiative_boundaries) D(right_extrap_press_multiplier) D(couple_J_into_T)
+#undef V
+#undef D
+    if (name == "BAND_IS_HIGHENERGY") { out.assign(p.BAND_IS_HIGHENERGY.begin(), p.BAND_IS_HIGHENERGY.end()); return true; }
+    if (name.size() > 2 && name[0] == 's') {
+        const size_t dot = name.find('.');
+        if (dot == std::string::npos) return false;
+        const int k = atoi(name.substr(1, dot - 1).c_str());
+        if (k < 0 || k >= (int)p.species.size()) return false;
+        const SpeciesData& sp = p.species[k];
+        const std::string f = name.substr(dot + 1);
+#define V(x) if (f == #x) { out = sp.x; return true; }
+#define D(x) if (f == #x) { out.assign(1, (double)sp.x); return true; }
+        V(u1) V(u2) V(u3) V(eint_last) V(opacity_avg_solar) V(opacity_avg_planck) V(opacity_avg_rosseland)
+        D(mass_amu) D(inv_mass) D(static_charge) D(initial_fraction) D(density_excess) D(is_dust_like) D(cv) D(gamma_adiabat)
+        D(degrees_of_freedom) D(const_T_space) D(const_opacity) D(boundary_left) D(boundary_right) D(USE_WAVE)
+#undef V
+#undef D
+        if (f == "SHOCK_TUBE_UL") { out.assign(sp.SHOCK_TUBE_UL, sp.SHOCK_TUBE_UL + 3); return true; }
+        if (f == "SHOCK_TUBE_UR") { out.assign(sp.SHOCK_TUBE_UR, sp.SHOCK_TUBE_UR + 3); return true; }
+        if (f == "BACKGROUND_U") { out.assign(sp.BACKGROUND_U, sp.BACKGROUND_U + 3); return true; }
+    }
+    return false;
+}
+
 }  // namespace aio

@@ -79,6 +79,7 @@ typedef std::map<std::string, std::vector<double>> DumpMap;
 // aiodump container (oracle/ref_dump.cpp): "<name> <count>\n" + count float64.
 bool read_dump(const std::string& path, DumpMap& out, std::string& err);
 bool problem_from_dump(const DumpMap& d, Problem& p, std::string& err);
+bool problem_field(const Problem& p, const std::string& name, std::vector<double>& out);
 
 // Front end: same three strings as the reference's c_Sim ctor (init_and_bounds.cpp:26).
 // overrides: "KEY value" pairs applied on top of the .par file for this column (ensemble sweeps).

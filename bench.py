@@ -171,7 +171,14 @@ def main():
 
     ncols, n_total = args.ncols, args.ncols * world
     overrides = [(c, "PARI_UVSTAR", repr(uv_value(rank + c * world, n_total))) for c in range(ncols)]   # interleaved: k -> GPU k mod G
-    ens = A.Ensemble.from_dump(os.path.join(GOLDEN, f"{CASE}_init.bin"), ncols=ncols, overrides=overrides, device=local)
+    # the reference-facing entry point: the deck's own .par/.spc/.opa files (oracle/decks holds the unmodified inputs of
+    # configs[3]); opacity files are opened relative to the CWD exactly as the reference does (io.cpp:143)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ROOT, "oracle", "decks"))
+    try:
+        ens = A.Ensemble.from_files(DECK_DIR, DECK_PAR, "", ncols=ncols, overrides=overrides, device=local)
+    finally:
+        os.chdir(cwd)
     N, S = ens.num_cells, ens.num_species
 
     def barrier():
@@ -259,8 +266,8 @@ def main():
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"{ncols}-column/GPU PARI_UVSTAR sweep of configs[3] {DECK_PAR} ({N} cells x {S} species, "
-                                       "order-2 hydro + 2-band irradiation + simple FLD), state from the reference constructor "
-                                       f"(tests/golden), {args.spinup} untimed spin-up steps",
+                                       "order-2 hydro + 2-band irradiation + simple FLD), built by aio_create from the deck's own .par/.spc/.opa, "
+                                       f"{args.spinup} untimed spin-up steps",
                            "columns_per_gpu": ncols, "num_cells": N, "num_species": S, "parallelism": f"columns x{world}",
                            "l2": "inputs larger than L2 (state ~%.0f MB per GPU)" % (ncols * (N + 2) * 8 * 9 / 1e6)},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline,

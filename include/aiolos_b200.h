@@ -85,6 +85,11 @@ int aio_status(aio_ensemble* e, int column, double* t, double* dt, long long* st
 int aio_status_all(aio_ensemble* e, double* t, double* dt, long long* steps, int* state);   /* arrays of ncols */
 int aio_get(aio_ensemble* e, int column, int species, int field, double* dst, int n);
 
+/* What the front end built for one column, by the reference's member name ("x_i12", "phi", "planck_matrix", "s0.u1",
+ * "s1.opacity_avg_solar", "dt", ...).  Returns the number of values (copies at most `capacity` into dst; dst may be NULL),
+ * or a negative error code. */
+int aio_problem_field(aio_ensemble* e, int column, const char* name, double* dst, int capacity);
+
 /* Conserved state of all columns, host layout [3][ncols][num_species][num_cells+2] (component, column, species, cell). */
 int aio_upload_state(aio_ensemble* e, const double* u_host);
 int aio_download_state(aio_ensemble* e, double* u_host);

@@ -104,3 +104,19 @@ def test_crashed_column_freezes_others_continue(lib):
     st = ens.status_all()
     assert st["state"][1] == 1 and st["steps"][1] == 1
     assert st["state"][0] == 0 and st["steps"][0] == 5 and st["steps"][2] == 5
+
+
+def test_from_files_matches_reference(lib, monkeypatch):
+    """The drop-in entry point on the GPU: configs[3] built from its own .par/.spc/.opa (oracle/decks holds the unmodified
+    inputs), 100 steps, against the reference's state; and the front end's arrays against the reference constructor's."""
+    from aiodump import read_dump
+    from conftest import ROOT
+    monkeypatch.chdir(os.path.join(ROOT, "oracle", "decks"))
+    ens = A.Ensemble.from_files("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", "", ncols=4, lib=lib)
+    init = read_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_init.bin"))
+    for name in ("x_i12", "vol", "phi", "planck_matrix", "solar_heating_final", "Jrad_FLD", "s0.u1", "s0.u3", "s0.opacity_avg_solar"):
+        a, b = ens.problem_field(name, 3), init[name]
+        assert a.shape == b.shape and np.allclose(a, b, rtol=2e-12, atol=0), name
+    ens.advance(100)
+    ref = read_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_k100.bin"))
+    assert max(compare_with_golden(ens, ref, column=2).values()) < 1e-8
