@@ -8,6 +8,7 @@
 #include "friction.cuh"
 #include "rad_simple.cuh"
 #include "rad_full.cuh"
+#include "step2.cuh"
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -27,6 +28,8 @@ struct Engine::Impl {
     size_t smem_hydro = 0, smem_rad = 0, smem_fric = 0;
     int nt_full = 0; size_t smem_full = 0;
     bool has_friction = false;
+    bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
+    size_t smem_rad2 = 0;
     long long launches = 0;
     std::vector<ColState> h_cs;
     double* pinned = nullptr; size_t pinned_bytes = 0;
@@ -142,6 +145,20 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.dx = im->upload(padded(q0.dx)); p.surf = im->upload(padded(q0.surf)); p.vol = im->upload(padded(q0.vol));
     p.omegaplus = im->upload(padded(q0.omegaplus)); p.omegaminus = im->upload(padded(q0.omegaminus));
     p.spp_left = im->upload(padded(q0.source_pressure_prefactor_left)); p.spp_right = im->upload(padded(q0.source_pressure_prefactor_right));
+    {   // grid-only factors of the slope limiter and the flux divergence (reconstruct.cpp:74-79, advection.cpp:503)
+        std::vector<double> cF(NP, 0.), cB(NP, 0.), ixF(NP, 0.), ixB(NP, 0.), wl(NP, 0.), wr(NP, 0.), iv(NP, 0.);
+        for (int i = 1; i <= N; i++) {
+            cF[i] = (q0.x_iVC[i + 1] - q0.x_iVC[i]) / (q0.x_i[i] - q0.x_iVC[i]);
+            cB[i] = (q0.x_iVC[i] - q0.x_iVC[i - 1]) / (q0.x_iVC[i] - q0.x_i[i - 1]);
+            ixF[i] = 1. / (q0.x_iVC[i + 1] - q0.x_iVC[i]);
+            ixB[i] = 1. / (q0.x_iVC[i] - q0.x_iVC[i - 1]);
+            wl[i] = q0.x_i[i - 1] - q0.x_iVC[i];
+            wr[i] = q0.x_i[i] - q0.x_iVC[i];
+            iv[i] = 1. / q0.vol[i];
+        }
+        p.g_cF = im->upload(cF); p.g_cB = im->upload(cB); p.g_idxF = im->upload(ixF); p.g_idxB = im->upload(ixB);
+        p.g_wl = im->upload(wl); p.g_wr = im->upload(wr); p.g_ivol = im->upload(iv);
+    }
     p.planck_matrix = im->upload(q0.planck_matrix); p.l_i_out = im->upload(q0.l_i_out);
     p.highenergy_switch = im->upload(q0.highenergy_switch);
     p.fric_mask = im->upload(q0.friction_coeff_mask); p.inv_totmasses = im->upload(q0.inv_totmasses);
@@ -212,6 +229,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.u = im->upload(hu); p.eint = im->upload(he); p.phi = im->upload(hphi); p.phis = im->upload(hphis);
     p.J = im->upload(hJ); p.solar_heating_final = im->upload(hsol); p.prim2v = im->upload(hp2);
     p.dS = im->dalloc<double>((size_t)ncol * S * NP);
+    p.dpm = im->dalloc<double>((size_t)ncol * S * NP); p.dpp = im->dalloc<double>((size_t)ncol * S * NP);
+    p.gsrc = im->dalloc<double>((size_t)ncol * S * NP);
     {   // dS_band(N, b) as the constructor left it: the first update_dS copies it into cell N+1 (radiation.cpp:263-265)
         std::vector<double> top((size_t)ncol * p.Bin, 0.0);
         for (int c = 0; c < ncol; c++)
@@ -237,11 +256,17 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_hydro = ((size_t)9 * N2 + 32 + 12 * p.ng) * sizeof(double);
     im->smem_rad = ((size_t)(5 * S + 7) * N2 + 32) * sizeof(double);
     im->smem_fric = 64 * sizeof(double);
+    im->smem_rad2 = ((size_t)(5 * S + 7) * N2 + 32 + 4 * NT) * sizeof(double);
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
         throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
 #define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
     SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
+    SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
+    if (p.use_rad_fluxes == 2) {
+        if (im->smem_rad2 > (size_t)maxsm) throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
+        SETSM(k_rad2<1>, im->smem_rad2); SETSM(k_rad2<2>, im->smem_rad2); SETSM(k_rad2<4>, im->smem_rad2); SETSM(k_rad2<8>, im->smem_rad2);
+    }
     if (p.use_rad_fluxes == 2) { SETSM(k_rad_simple<1>, im->smem_rad); SETSM(k_rad_simple<2>, im->smem_rad); SETSM(k_rad_simple<4>, im->smem_rad); SETSM(k_rad_simple<8>, im->smem_rad); }
 #undef SETSM
     AIO_LAUNCH(k_prime, ncol, 256, 0, im->stream, p);
@@ -274,6 +299,14 @@ void Engine::launch_step() {
     const bool prof = im->prof_on;
     auto mark = [&](int k) { if (prof) CK(cudaEventRecord(im->prof_ev[k], im->stream)); };
     mark(0);
+    if (im->v2) {
+        switch (im->CPT) {
+        case 1: AIO_LAUNCH(k_hydro2<1>, ncol, NT, im->smem_hydro, im->stream, p); break;
+        case 2: AIO_LAUNCH(k_hydro2<2>, ncol, NT, im->smem_hydro, im->stream, p); break;
+        case 4: AIO_LAUNCH(k_hydro2<4>, ncol, NT, im->smem_hydro, im->stream, p); break;
+        default: AIO_LAUNCH(k_hydro2<8>, ncol, NT, im->smem_hydro, im->stream, p); break;
+        }
+    } else
     switch (im->CPT) {
     case 1: AIO_LAUNCH(k_hydro<1>, ncol, NT, im->smem_hydro, im->stream, p); break;
     case 2: AIO_LAUNCH(k_hydro<2>, ncol, NT, im->smem_hydro, im->stream, p); break;
@@ -284,7 +317,15 @@ void Engine::launch_step() {
     mark(1);
     if (im->has_friction) { launch_friction(); im->launches++; }
     mark(2);
-    if (p.use_rad_fluxes == 2) {
+    if (p.use_rad_fluxes == 2 && im->v2) {
+        switch (im->CPT) {
+        case 1: AIO_LAUNCH(k_rad2<1>, ncol, NT, im->smem_rad2, im->stream, p); break;
+        case 2: AIO_LAUNCH(k_rad2<2>, ncol, NT, im->smem_rad2, im->stream, p); break;
+        case 4: AIO_LAUNCH(k_rad2<4>, ncol, NT, im->smem_rad2, im->stream, p); break;
+        default: AIO_LAUNCH(k_rad2<8>, ncol, NT, im->smem_rad2, im->stream, p); break;
+        }
+        im->launches++;
+    } else if (p.use_rad_fluxes == 2) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad_simple<1>, ncol, NT, im->smem_rad, im->stream, p); break;
         case 2: AIO_LAUNCH(k_rad_simple<2>, ncol, NT, im->smem_rad, im->stream, p); break;
@@ -366,6 +407,11 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         if (value == "thomas") im->p.tridiag_serial = 1;
         else if (value == "pcr") im->p.tridiag_serial = 0;
         else throw std::invalid_argument("option tridiag: expected 'pcr' or 'thomas'");
+    } else if (key == "kernels") {
+        if (value == "v1") im->v2 = false;
+        else if (value == "v2") im->v2 = true;
+        else throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
+        if (total_steps() != 0) throw std::invalid_argument("option kernels must be set before the first step");
     } else throw std::invalid_argument("unknown option '" + key + "'");
 }
 long long Engine::total_steps() {
