@@ -29,7 +29,7 @@ struct Engine::Impl {
     int nt_full = 0; size_t smem_full = 0;
     bool has_friction = false;
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
-    size_t smem_rad2 = 0;
+    size_t smem_rad2 = 0, smem_rad3 = 0;
     long long launches = 0;
     std::vector<ColState> h_cs;
     double* pinned = nullptr; size_t pinned_bytes = 0;
@@ -257,6 +257,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_rad = ((size_t)(5 * S + 7) * N2 + 32) * sizeof(double);
     im->smem_fric = 64 * sizeof(double);
     im->smem_rad2 = ((size_t)(5 * S + 7) * N2 + 32 + 4 * NT) * sizeof(double);
+    im->smem_rad3 = ((size_t)7 * N2 + 32 + 4 * NT) * sizeof(double);
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
         throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
@@ -265,6 +266,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
         if (im->smem_rad2 > (size_t)maxsm) throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
+        SETSM(k_rad3<1>, im->smem_rad3); SETSM(k_rad3<2>, im->smem_rad3); SETSM(k_rad3<4>, im->smem_rad3); SETSM(k_rad3<8>, im->smem_rad3);
         SETSM(k_rad2<1>, im->smem_rad2); SETSM(k_rad2<2>, im->smem_rad2); SETSM(k_rad2<4>, im->smem_rad2); SETSM(k_rad2<8>, im->smem_rad2);
     }
     if (p.use_rad_fluxes == 2) { SETSM(k_rad_simple<1>, im->smem_rad); SETSM(k_rad_simple<2>, im->smem_rad); SETSM(k_rad_simple<4>, im->smem_rad); SETSM(k_rad_simple<8>, im->smem_rad); }
@@ -317,7 +319,15 @@ void Engine::launch_step() {
     mark(1);
     if (im->has_friction) { launch_friction(); im->launches++; }
     mark(2);
-    if (p.use_rad_fluxes == 2 && im->v2) {
+    if (p.use_rad_fluxes == 2 && im->v2 && p.S == 1 && !p.Tsave) {
+        switch (im->CPT) {
+        case 1: AIO_LAUNCH(k_rad3<1>, ncol, NT, im->smem_rad3, im->stream, p); break;
+        case 2: AIO_LAUNCH(k_rad3<2>, ncol, NT, im->smem_rad3, im->stream, p); break;
+        case 4: AIO_LAUNCH(k_rad3<4>, ncol, NT, im->smem_rad3, im->stream, p); break;
+        default: AIO_LAUNCH(k_rad3<8>, ncol, NT, im->smem_rad3, im->stream, p); break;
+        }
+        im->launches++;
+    } else if (p.use_rad_fluxes == 2 && im->v2) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad2<1>, ncol, NT, im->smem_rad2, im->stream, p); break;
         case 2: AIO_LAUNCH(k_rad2<2>, ncol, NT, im->smem_rad2, im->stream, p); break;

@@ -273,8 +273,11 @@ __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col
     }
 }
 
+#ifndef AIO_HYDRO2_MINB
+#define AIO_HYDRO2_MINB 3
+#endif
 template <int CPT>
-__global__ void __launch_bounds__(256, 2) k_hydro2(DevParams p) {
+__global__ void __launch_bounds__(256, AIO_HYDRO2_MINB) k_hydro2(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int col = blockIdx.x;
     const StepInfo si = step_head(p, col);
@@ -578,6 +581,232 @@ __global__ void __launch_bounds__(256, 2) k_rad2(DevParams p) {
     const ColState& c = p.cs[col];
     if (!c.in_step) return;
     rad_simple_phase_v2<CPT>(p, col, sm, c.dt, c.t);
+}
+
+// ---- single-species radiation phase ("v3"): own-cell quantities live in registers, 7 shared arrays (3 CTAs per SM) ----------------
+// Same arithmetic as rad_simple_phase_v2 for S == 1; thread t owns cells t, t+NT, ... in every loop, so rho, T, dS never go
+// through shared memory, and eta1 / 1/denom / T are parked in the shared arrays that are dead while the J system is solved.
+template <int CPT>
+__device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col, double* sm, const double ddt, const double tnow) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = p.N, N2 = p.N2, Bin = p.Bin;
+    double* TO = sm;                   // total_opacity (out band 0); parks eta1 during the solve
+    double* JJ = TO + N2;              // J; parks T during the solve
+    double* TAU = JJ + N2;             // scan workspace, then the interface diffusion coefficients; parks 1/denom during the solve
+    double* A = TAU + N2; double* B = A + N2; double* C = B + N2; double* D = C + N2;
+    double* red = D + N2;              // 32 + 4*NT
+    const int KA = Bin + 2 * p.Bout;
+    const SpeciesConst sc = p.sp[0];
+    const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1, icv = 1.0 / sc.cv;
+    double* __restrict__ U1 = p.u + idx_u(p, 0, col, 0, 0);
+    double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
+    double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
+    double* __restrict__ Jg = p.J + idx_J(p, col, 0, 0);
+    double rho[CPT], T[CPT], dS[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        rho[k] = 1; T[k] = 1; dS[k] = 0;
+        if (j < N2) {
+            const double a1 = U1[j], a2 = U2[j], a3 = U3[j];
+            const double rin = frcp(a1), v = a2 * rin;
+            rho[k] = a1;
+            T[k] = gm1 * (a3 - 0.5 * a2 * v) * rin * igm1 * icv;
+            JJ[j] = Jg[j];
+        }
+    }
+    __syncthreads();
+    // ---- stellar heating (radiation.cpp:43-348) -------------------------------------------------------------------------------------
+    for (int b = 0; b < Bin; b++) {
+        double F = p.solar_heating_final[(size_t)col * Bin + b];
+        if (tnow < p.radiation_rampup_time)
+            F = F * (p.init_radiation_factor + (1. - p.init_radiation_factor) * tnow / p.radiation_rampup_time);
+        const double top_prev = p.dSband_top[(size_t)col * Bin + b];
+        const double kap = p.kappa_avg[b], hsw = p.highenergy_switch[b];
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j >= 1 && j <= N) TAU[N - j] = (kap * rho[k]) * __ldg(p.dx + j);
+        }
+        __syncthreads();
+        block_inclusive_scan(TAU, N, red);
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j >= 1 && j <= N + 1) {
+                const double dxj = __ldg(p.dx + j);
+                const double cell_tau = (kap * rho[k]) * dxj;
+                double dSb;
+                if (j < N + 1) {
+                    const double rad_j = TAU[N - j];
+                    const double rad_jp = (j == N) ? 0. : TAU[N - j - 1];
+                    const double Sb = F * exp(-rad_jp);
+                    dSb = 0.25 * Sb * frcp(dxj) * (1. - p.bond_albedo);
+                    const double dtau_tot = -(rad_jp - rad_j);
+                    if (dtau_tot > 1e-3) dSb *= (-expm1(-dtau_tot));
+                    else dSb *= (-fastexpm1_2(-dtau_tot));
+                    dSb = smax(dSb, 0.);
+                } else {
+                    dSb = top_prev;
+                }
+                if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
+                const double frac = hsw * kap * rho[k] * dxj * frcp(cell_tau);
+                double v = dS[k] + hsw * dSb * frac;
+                if (v < 1e-50) v = 0.;
+                dS[k] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- thermal band: total opacity, interface diffusion coefficients ------------------------------------------------------------------
+    {
+        const double kR = p.kappa_avg[Bin + p.Bout + 0];
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < N2) TO[j] = (j >= 1) ? fmax(kR * rho[k], 0.) : 0.;
+        }
+    }
+    __syncthreads();
+    double* DF = TAU;
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int jj = tid + k * NT;
+        if (jj < N2) {
+            double Dv = 0;
+            if (jj >= 1 && jj <= N) {
+                const double dxc = (__ldg(p.x_i12 + jj + 1) - __ldg(p.x_i12 + jj));
+                const double t0 = TO[jj], t1 = TO[jj + 1];
+                double rhokr = smax(2. * (t0 * t1) * frcp(t0 + t1), 4. / 3. * frcp(dxc));
+                rhokr = smin(0.5 * (t0 + t1), rhokr);
+                const double tau_inv = frcp(dxc * rhokr);
+                const double dJ = fabs(JJ[jj + 1] - JJ[jj]) * frcp(JJ[jj] + 1e-300);
+                const double R = p.xi_rad * tau_inv * dJ;
+                const double fl = (R <= 2) ? 2 * frcp(3 + fsqrt(9 + 10 * R * R)) : 10 * frcp(10 * R + 9 + fsqrt(81 + 180 * R));
+                Dv = tau_inv * __ldg(p.surf + jj) * fl;
+            }
+            DF[jj] = Dv;
+        }
+    }
+    __syncthreads();
+    // ---- FLD-simple assembly (radiation_simple.cpp:44-233) ----------------------------------------------------------------------------------
+    const double icdt = frcp(C_CLIGHT * ddt);
+    const double kP = p.kappa_avg[Bin + 0];
+    const double eta2 = 4. * C_PI * ddt * kP * p.no_rad_trans * icv;
+    double e1[CPT], idn[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        e1[k] = 0; idn[k] = 1;
+        if (j < N2) {
+            double l = 0, d = 0, u = 0, r = 0;
+            if (j >= 2 && j <= N + 1) { const double Dm = DF[j - 1]; d = Dm; l = -Dm; }
+            if (j <= N) {
+                const double tv = __ldg(p.vol + j) * icdt;
+                d += tv;
+                r += tv * JJ[j];
+            }
+            if (j >= 1 && j <= N) { const double Dj = DF[j]; u = -Dj; d += Dj; }
+            if (j < p.ng) { l = 0; u = -d; r = 0; }
+            if (p.closed_radiative_boundaries) {
+                if (j >= N2 - p.ng) { l = -l; u = 0; r = 0; }
+            } else if (j == N) {
+                double f = 1. / p.xi_rad * __ldg(p.x_i12 + N) / __ldg(p.x_i12 + N + 1);
+                if (p.geometry == 0) f = 1;
+                else if (p.geometry == 2) f *= f;
+                l = -f * d; u = 0; r = 0;
+            }
+            if (j <= N) {
+                const double Ts = T[k], Ts3 = Ts * Ts * Ts, rhos = rho[k];
+                const double fac = ddt * p.no_rad_trans * kP * icv * C_SIGMA_RAD * Ts3;
+                const double in_ = frcp(1. + 16. * fac);
+                double eta1 = Ts * (1. + 12. * fac);
+                eta1 += ddt * dS[k] * frcp(rhos) * icv;
+                e1[k] = eta1; idn[k] = in_;
+                // same (cancelling) form as radiation_simple.cpp:210-211: its round-off is part of what the reference computes
+                const double exd = p.no_rad_trans * rhos * kP * (1 - 4. * C_SIGMA_RAD * Ts3 / C_PI * eta2 * in_);
+                const double exr = p.no_rad_trans * rhos * kP * C_SIGMA_RAD * Ts3 / C_PI * (4 * eta1 * in_ - 3 * Ts);
+                d += __ldg(p.vol + j) * exd;
+                r += __ldg(p.vol + j) * exr;
+            }
+            A[j] = l; B[j] = d; C[j] = u; D[j] = r;
+            p.dS[idx_s(p, col, 0, j)] = dS[k];
+        }
+    }
+    __syncthreads();
+    // park the own-cell values that must survive the solve in arrays that are dead now
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        if (j < N2) { TO[j] = e1[k]; TAU[j] = idn[k]; JJ[j] = T[k]; }
+    }
+    if (p.tridiag_serial) {
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < N2; i++) { const double m = A[i] / B[i - 1]; B[i] -= m * C[i - 1]; D[i] -= m * D[i - 1]; }
+            D[N2 - 1] /= B[N2 - 1];
+            for (int i = N2 - 2; i >= 0; i--) D[i] = (D[i] - C[i] * D[i + 1]) / B[i];
+        }
+        __syncthreads();
+    } else {
+        tridiag_substructured<CPT>(A, B, C, D, N2, red + 32);
+    }
+    // ---- J, T update, e <- T, p <- e, cons <- prim, step tail ------------------------------------------------------------------------------------
+    int jneg = 0;
+    double Jn[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        Jn[k] = 0;
+        if (j < N2) {
+            Jn[k] = p.solve_for_j ? D[j] : Jg[j];
+            if (Jn[k] < 0. && p.couple_J_into_T) jneg = 1;
+        }
+    }
+    const int Jswitch = block_or(jneg) || (tnow > 1e15);
+    TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
+    int negJ = 0; double negJval = 0;
+    const bool allowJ = p.use_planetary_temperature && (D[N] > 0);
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        if (j < N2) {
+            double Jv = Jn[k];
+            if (p.couple_J_into_T && j <= N - 1 && Jv < 0) {
+                if (Jv > -1e-10) Jv *= -1.;
+                else if (!(j < N && allowJ)) { negJ = 1; negJval = Jv; }
+            }
+            Jg[j] = Jv;
+            const double a1 = U1[j], a2 = U2[j], a3 = U3[j];
+            const double rin = frcp(a1), v = a2 * rin;
+            const double pr = gm1 * (a3 - 0.5 * a2 * v);
+            const double e_old = pr * rin * igm1;
+            const double cs_old = fsqrt((gm1 + 1) * gm1 * e_old);
+            double Tn = JJ[j];
+            if (j <= N) {
+                double tt = TO[j] * TAU[j];
+                if (p.couple_J_into_T) tt += eta2 * TAU[j] * Jn[k];
+                if (tt < p.temperature_floor) tt = p.temperature_floor;
+                if (Jswitch == 0) Tn = tt;
+            }
+            const double e = Tn * sc.cv;
+            const double pn = e * a1 * gm1;
+            const double m2 = a1 * v;
+            U2[j] = m2; U3[j] = pn * igm1 + 0.5 * m2 * v;
+            tail_cell(p, col, 0, j, v, cs_old, e, Tn, acc);
+        }
+    }
+    negJ = block_or(negJ);
+    tail_commit(p, col, acc, red, negJ != 0, negJval);
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
+    AIO_DYN_SMEM(double, sm);
+    const int col = blockIdx.x;
+    const ColState& c = p.cs[col];
+    if (!c.in_step) return;
+    rad1_phase_v3<CPT>(p, col, sm, c.dt, c.t);
 }
 
 }  // namespace aio
