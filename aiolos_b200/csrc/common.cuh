@@ -91,7 +91,7 @@ struct DevParams {
     double *dSband_top;                 // [ncol][Bin] dS_band(N,b) of the previous step (radiation.cpp:263-265)
     // v2 kernels (step2.cuh): tabulated slope-limiter factors / inverse volumes [NP], shared by all columns, and the static
     // per-column hydrostatic offsets and gravity source coefficient [ncol][S][NP]
-    const double *g_cF, *g_cB, *g_idxF, *g_idxB, *g_wl, *g_wr, *g_ivol;
+    const double *g_cF, *g_cB, *g_idxF, *g_idxB, *g_wl, *g_wr, *g_ivol, *g_idx;
     double *dpm, *dpp, *gsrc;
     double *Xstore;                     // full FLD: [ncol][N2][n][Bout+1]  X_i = S_i^-1 u_i and S_i^-1 rhs_i (rad_full.cuh)
     double *Tsave, *cssave;             // [ncol][S][NP] prim.temperature / prim.sound_speed as left by the post-hydro

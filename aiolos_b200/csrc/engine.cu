@@ -156,6 +156,9 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
             wr[i] = q0.x_i[i] - q0.x_iVC[i];
             iv[i] = 1. / q0.vol[i];
         }
+        std::vector<double> ix(NP, 1.);
+        for (int i = 0; i < N2; i++) ix[i] = 1. / q0.dx[i];
+        p.g_idx = im->upload(ix);
         p.g_cF = im->upload(cF); p.g_cB = im->upload(cB); p.g_idxF = im->upload(ixF); p.g_idxB = im->upload(ixB);
         p.g_wl = im->upload(wl); p.g_wr = im->upload(wr); p.g_ivol = im->upload(iv);
     }

@@ -49,6 +49,15 @@ inline double fsqrt(double x) { return std::sqrt(x); }
 #endif
 __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b); }
 
+// Per-cell tail (helpers.cpp:28-71, advection.cpp:88-91,282-307) with branch-free reciprocals and the tabulated 1/dx.
+__device__ __forceinline__ void tail_cell2(const DevParams& p, double* __restrict__ eint_row, int j, double v, double cs, double eint,
+                                           double T, TailAcc& a) {
+    if (j >= 1 && j <= p.N - 1) a.maxde = fmax(a.maxde, fabs(eint_row[j] - eint) * frcp(eint));
+    if (j >= 1 && j <= p.N) { const double ix = __ldg(p.g_idx + j); a.minstep = fmax(a.minstep, fabs(v * ix) + cs * ix); }
+    if (j <= p.N - 1 && (T < 0 || isnan(T))) { a.bad = 1; a.badval = T; }
+    if (j <= p.N) eint_row[j] = eint;
+}
+
 // ---- static per-column tables: dp-(i), dp+(i) (aiolos.h:1003-1016) and the gravity source coefficient (source.cpp:157-164) ------
 __device__ inline void build_static_tables(const DevParams& p, const int col) {
     const int tid = threadIdx.x, NT = blockDim.x, N = p.N, N2 = p.N2;
@@ -265,7 +274,7 @@ __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col
                     const double v = u2[k] * rin;
                     const double pr = gm1 * (u3[k] - 0.5 * u2[k] * v);
                     const double e = pr * rin * igm1;
-                    tail_cell(p, col, s, j, v, fsqrt((gm1 + 1) * gm1 * e), e, e / sc.cv, acc);
+                    tail_cell2(p, p.eint + idx_s(p, col, s, 0), j, v, fsqrt((gm1 + 1) * gm1 * e), e, e / sc.cv, acc);
                 }
             }
         }
@@ -602,6 +611,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
     double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
     double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
     double* __restrict__ Jg = p.J + idx_J(p, col, 0, 0);
+    double* __restrict__ EI = p.eint + idx_s(p, col, 0, 0);
     double rho[CPT], T[CPT], dS[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; k++) {
@@ -793,7 +803,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
             const double pn = e * a1 * gm1;
             const double m2 = a1 * v;
             U2[j] = m2; U3[j] = pn * igm1 + 0.5 * m2 * v;
-            tail_cell(p, col, 0, j, v, cs_old, e, Tn, acc);
+            tail_cell2(p, EI, j, v, cs_old, e, Tn, acc);
         }
     }
     negJ = block_or(negJ);
