@@ -156,6 +156,10 @@ def main():
         reference_arm(args, rank)
         return
 
+    # everything but the final JSON line goes to stderr (NCCL prints its version banner on fd 1)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import aiolos_b200 as A
@@ -272,7 +276,10 @@ def main():
                            "l2": "inputs larger than L2 (state ~%.0f MB per GPU)" % (ncols * (N + 2) * 8 * 9 / 1e6)},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline,
                 "cpu_baseline": cpu}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if dist:
         dist.destroy_process_group()
 
