@@ -66,6 +66,8 @@ struct DevParams {
     int use_rad_fluxes, friction_solver, use_collisional_heating, photochemistry_level;
     int closed_radiative_boundaries, use_planetary_temperature, couple_J_into_T, solve_for_j;
     int radiation_matter_equilibrium_test, use_total_pressure, collision_model, opacity_model;
+    int use_avg_temperature, update_coll_frequently;
+    double avg_temperature_t0, avg_temperature_t1;
     int last_kernel;            // 0 hydro, 1 friction, 2 radiation: who runs the step tail
     int tridiag_serial;         // 1: scalar J system solved in the reference's Thomas order on one lane (validation mode)
     // scalars

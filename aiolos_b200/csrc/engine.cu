@@ -88,11 +88,10 @@ static void check_supported(const Problem& q) {
     if (q.radiation_matter_equilibrium_test != 0) fail("RAD_MATTER_EQUI_TEST != 0");
     if (q.use_rad_fluxes < 0 || q.use_rad_fluxes > 2) fail("PARI_USE_RADIATION outside 0..2");
     if (q.use_rad_fluxes == 2 && q.num_bands_out != 1) fail("simple FLD solver needs NUM_BANDS_OUT 1");
-    if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating) fail("simple FLD + collisional heating with >1 species");
-    if (q.use_rad_fluxes == 1 && q.num_species > 1 && q.use_collisional_heating) fail("full FLD + collisional heating with >1 species");
+    if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && q.num_species > 8) fail("simple FLD + collisional heating with more than 8 species");
+    if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && !q.update_coll_frequently) fail("UPDATE_COLL_FREQUENTLY 0");
     if (q.use_rad_fluxes && q.opacity_model != 'C' && q.opacity_model != 'P') fail(std::string("opacity model ") + q.opacity_model);
     if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
-    if (q.use_avg_temperature) fail("USE_AVG_T 1");
     if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
     for (auto& sp : q.species) {
         if (sp.boundary_left == 0 || sp.boundary_right == 0) fail("user boundary hooks (compile a problem plugin, INTEGRATION.md)");
@@ -125,6 +124,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.couple_J_into_T = q0.couple_J_into_T; p.solve_for_j = q0.solve_for_j;
     p.radiation_matter_equilibrium_test = q0.radiation_matter_equilibrium_test; p.use_total_pressure = q0.use_total_pressure;
     p.collision_model = q0.collision_model; p.opacity_model = q0.opacity_model;
+    p.use_avg_temperature = q0.use_avg_temperature; p.update_coll_frequently = q0.update_coll_frequently;
+    p.avg_temperature_t0 = q0.avg_temperature_t0; p.avg_temperature_t1 = q0.avg_temperature_t1;
     im->has_friction = (q0.friction_solver >= 0 && S > 1);     // compute_drag_update, source.cpp:233-243
     p.last_kernel = q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
     p.max_timestep_change = q0.max_timestep_change; p.dt_min_init = q0.dt_min_init; p.dt_max = q0.dt_max;
@@ -330,7 +331,7 @@ void Engine::launch_step() {
         default: AIO_LAUNCH(k_rad3<8>, ncol, NT, im->smem_rad3, im->stream, p); break;
         }
         im->launches++;
-    } else if (p.use_rad_fluxes == 2 && im->v2) {
+    } else if (p.use_rad_fluxes == 2 && im->v2 && !(p.use_collisional_heating && p.S > 1)) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad2<1>, ncol, NT, im->smem_rad2, im->stream, p); break;
         case 2: AIO_LAUNCH(k_rad2<2>, ncol, NT, im->smem_rad2, im->stream, p); break;

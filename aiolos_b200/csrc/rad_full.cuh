@@ -232,6 +232,26 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
                 rhs += 12 * C_PI * fac * Ts / sc.cv;
             }
             A[lane * LD + lane] = d;
+            // collisional T_i - T_j coupling (radiation.cpp:589-615, source.cpp:656-674)
+            if (p.use_collisional_heating && S > 1) {
+                double tot0 = 0;
+                if (i >= 1) for (int ss = 0; ss < S; ss++) tot0 = fmax(kap[ss * KA + Bin + Bout + 0] * p.u[idx_u(p, 0, col, ss, i)], tot0);
+                const double tau = tot0 * (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+                const double damp = (tau < 1e3) ? 1. : 1.e-4;
+                double diag_sum = 0, self = 0;
+                for (int sj = 0; sj < S; sj++) {
+                    const SpeciesConst cj = p.sp[sj];
+                    const double w1 = p.u[idx_u(p, 0, col, sj, i)], w2 = p.u[idx_u(p, 1, col, sj, i)], w3 = p.u[idx_u(p, 2, col, sj, i)];
+                    Prim3 qj = cons_to_prim(w1, w2, w3, cj.gm1);
+                    const double Tj = p.Tsave ? p.Tsave[idx_s(p, col, sj, i)] : eint_of(qj.p, qj.rho, cj.gm1) / cj.cv;
+                    double fc = p.fric_mask[s * S + sj] * alpha_pair(p, s, sj, S, sc, cj, u1, w1, w1 / cj.mass, Ts, Tj, tnow);
+                    fc *= 3 * C_KB / (sc.cv * (sc.mass + cj.mass));
+                    diag_sum += fc;
+                    if (sj == s) self = fc;
+                    else A[lane * LD + Bout + sj] -= fc * damp;
+                }
+                A[lane * LD + lane] -= (self - diag_sum) * damp;
+            }
         }
         // S_i = d_i - l_i X_{i-1} ;  rhs_i - l_i A_{i-1}   (only J rows have l entries)
         if (isJ && i > 0 && l_rr != 0.) {

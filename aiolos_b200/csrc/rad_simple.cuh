@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "hydro.cuh"
+#include "friction.cuh"
 
 namespace aio {
 
@@ -264,6 +265,70 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
             else if (!(j < N && p.use_planetary_temperature && JJ[N] > 0)) { negJ = 1; negJval = Jv; }
         }
         p.J[idx_J(p, col, 0, j)] = Jv;
+        // ---- T_i - T_j coupling through collisions (radiation_simple.cpp:316-447): one implicit SxS solve per cell -------------
+        constexpr int SC8 = 8;
+        double Tcoll[SC8];
+        const bool collheat = p.use_collisional_heating && S > 1;
+        if (collheat && j <= N) {
+            double M[SC8][SC8], b[SC8], rho8[SC8], T8[SC8], nd8[SC8];
+#pragma unroll
+            for (int si = 0; si < SC8; si++) {
+                if (si < S) { rho8[si] = RHO[si * N2 + j]; T8[si] = TT[si * N2 + j]; nd8[si] = rho8[si] / p.sp[si].mass; }
+                else { rho8[si] = 1; T8[si] = 1; nd8[si] = 0; }
+            }
+#pragma unroll
+            for (int si = 0; si < SC8; si++) {
+#pragma unroll
+                for (int sj = 0; sj < SC8; sj++) M[si][sj] = (si == sj && si >= S) ? 1. : 0.;
+                b[si] = 0.;
+                if (si < S) {
+                    const SpeciesConst ci = p.sp[si];
+                    const double kappa = p.kappa_avg[si * KA + Bin + 0];
+                    const double eta2 = 4. * C_PI * ddt * kappa * p.no_rad_trans / ci.cv;
+                    M[si][si] += DEN[si * N2 + j];
+                    if (p.couple_J_into_T) b[si] += eta2 * JJ[j];
+                    b[si] += E1[si * N2 + j];
+                    double diag_sum = 0;
+#pragma unroll
+                    for (int sj = 0; sj < SC8; sj++) {
+                        if (sj < S) {
+                            const double a = p.fric_mask[si * S + sj] *
+                                             alpha_pair(p, si, sj, S, ci, p.sp[sj], rho8[si], rho8[sj], nd8[sj], T8[si], T8[sj], tnow);
+                            const double temp = ddt * a * 3 * C_KB / (ci.cv * (ci.mass + p.sp[sj].mass));
+                            diag_sum += temp;
+                            M[si][sj] -= temp;
+                        }
+                    }
+                    M[si][si] += diag_sum;
+                }
+            }
+            lu_solve<SC8>(M, b, S);
+            double avg_nom = 0, avg_den = 0;
+#pragma unroll
+            for (int si = 0; si < SC8; si++) {
+                if (si < S) {
+                    const SpeciesConst ci = p.sp[si];
+                    double tt = b[si];
+                    if (tt < p.temperature_floor) tt = p.temperature_floor;
+                    if (tt > p.max_temperature) tt = p.max_temperature;
+                    if (j <= 4) tt = ci.const_T_space;
+                    avg_nom += rho8[si] * ci.cv * tt;
+                    avg_den += rho8[si] * ci.cv;
+                    Tcoll[si] = (tnow > 1e-10) ? tt : ci.const_T_space;
+                }
+            }
+            // radiation_simple.cpp:432-444, literally (with USE_AVG_T 0 the else branch runs, and avg_temperature_t1 defaults to 1e99)
+            if (p.use_avg_temperature && tnow < p.avg_temperature_t1) {
+                if (tnow < p.avg_temperature_t0) {
+#pragma unroll
+                    for (int si = 0; si < SC8; si++) if (si < S) Tcoll[si] = avg_nom / avg_den;
+                }
+            } else {
+#pragma unroll
+                for (int si = 0; si < SC8; si++)
+                    if (si < S) Tcoll[si] = avg_nom / avg_den * (1. - tnow / p.avg_temperature_t1) + Tcoll[si] * tnow / p.avg_temperature_t1;
+            }
+        }
         for (int s = 0; s < S; s++) {
             const SpeciesConst sc = p.sp[s];
             const double u1 = p.u[idx_u(p, 0, col, s, j)], u2 = p.u[idx_u(p, 1, col, s, j)], u3 = p.u[idx_u(p, 2, col, s, j)];
@@ -272,7 +337,8 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
             // stale sound speed seen by the next CFL estimate (neither friction nor radiation refresh prim.sound_speed)
             const double cs_old = p.cssave ? p.cssave[idx_s(p, col, s, j)] : cs_of(e_old, sc.gm1);
             double T = TT[s * N2 + j];
-            if (j <= N && p.radiation_matter_equilibrium_test <= 2) {
+            if (collheat) { if (j <= N) T = Tcoll[s]; }
+            else if (j <= N && p.radiation_matter_equilibrium_test <= 2) {
                 const double kappa = p.kappa_avg[s * KA + Bin + 0];
                 const double eta2 = 4. * C_PI * ddt * kappa * p.no_rad_trans / sc.cv;
                 double tt = E1[s * N2 + j] / DEN[s * N2 + j];

@@ -31,6 +31,10 @@ CASES = {
     "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc", [1, 100, 1000]),
     # configs[2]: 22-band full FLD
     "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc", [1, 20, 100, 1000]),
+    # configs[3] made two-species at lower resolution (our variant): n-n friction + simple FLD with collisional T_i-T_j coupling
+    "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", None, [1, 100, 1000]),
+    # the same with the full FLD solver: 3x3 blocks (J, T_1, T_2) with the collisional T-T coupling of radiation.cpp:589-615
+    "c6_dynamic3_2spc_fullfld": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_fullfld.par", None, [1, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
 }
@@ -45,6 +49,7 @@ def run_case(name):
     subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), RUN], check=True, stdout=subprocess.DEVNULL)
     for f in os.listdir(os.path.join(HERE, "decks")):        # our own deck variants live next to the reference's test decks
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "test_files", f)], check=True)
+        subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "runs_mdot_vs_euv_plot", f)], check=True)
     for k in steps:
         out = os.path.join(RUN, f"{name}_k{k}")
         cmd = [DUMP, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]

@@ -14,6 +14,8 @@ CASES = [
     ("c2m_friction_6spc_mild", 1, 1e-10), ("c2m_friction_6spc_mild", 100, 1e-8), ("c2m_friction_6spc_mild", 1000, 1e-8),
     ("c4_dynamic3_euv", 1, 1e-10), ("c4_dynamic3_euv", 100, 1e-8),
     ("c3_searth_22b", 1, 1e-10), ("c3_searth_22b", 20, 1e-8),
+    ("c5_dynamic3_2spc_collheat", 1, 1e-10), ("c5_dynamic3_2spc_collheat", 100, 1e-8),
+    ("c6_dynamic3_2spc_fullfld", 1, 1e-10), ("c6_dynamic3_2spc_fullfld", 100, 1e-8),
 ]
 
 

@@ -17,6 +17,7 @@ DECKS = {   # case -> (deck dir, par, spc)
     "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc"),
     "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc"),
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", ""),
+    "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", ""),
 }
 ARRAYS = ["x_i", "x_i12", "x_iVC", "dx", "surf", "vol", "omegaplus", "omegaminus", "source_pressure_prefactor_left",
           "source_pressure_prefactor_right", "phi", "l_i_in", "l_i_out", "photon_energies", "solar_heating_final",
@@ -38,6 +39,7 @@ def rundir(tmp_path_factory):
     subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), d], check=True, stdout=subprocess.DEVNULL)
     for f in os.listdir(os.path.join(GOLDEN, "decks")):
         shutil.copy(os.path.join(GOLDEN, "decks", f), os.path.join(d, "test_files", f))
+        shutil.copy(os.path.join(GOLDEN, "decks", f), os.path.join(d, "runs_mdot_vs_euv_plot", f))
     return d
 
 
