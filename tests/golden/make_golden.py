@@ -29,6 +29,9 @@ CASES = {
     # same deck made well-conditioned (T ~ 300 K, alpha*dt ~ 1): the shipped one starts at T ~ 1e-8 K where alpha*dt ~ 1e14
     # and the reference's own LU result depends on FMA contraction (README.md in this directory)
     "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc", [1, 100, 1000]),
+    # gas + dust sound wave of the reference's own test suite: dust species (pressureless Riemann solver, advection.cpp:623-650),
+    # constant collision model, problem 3 initial conditions, second order, periodic boundaries
+    "d1_dustywave_nonstiff": ("test_files/", "dustywave_nonstiff.par", "hydrogen.spc", [1, 100, 800]),
     # configs[2]: 22-band full FLD
     "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc", [1, 20, 100, 1000]),
     # configs[3] made two-species at lower resolution (our variant): n-n friction + simple FLD with collisional T_i-T_j coupling

@@ -16,6 +16,7 @@ CASES = [
     ("c3_searth_22b", 1, 1e-10), ("c3_searth_22b", 20, 1e-8),
     ("c5_dynamic3_2spc_collheat", 1, 1e-10), ("c5_dynamic3_2spc_collheat", 100, 1e-8),
     ("c6_dynamic3_2spc_fullfld", 1, 1e-10), ("c6_dynamic3_2spc_fullfld", 100, 1e-8),
+    ("d1_dustywave_nonstiff", 1, 1e-10), ("d1_dustywave_nonstiff", 100, 1e-8), ("d1_dustywave_nonstiff", 800, 1e-8),
 ]
 
 

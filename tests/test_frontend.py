@@ -17,6 +17,7 @@ DECKS = {   # case -> (deck dir, par, spc)
     "c2m_friction_6spc_mild": ("test_files/", "friction_6spc_mild.par", "friction_6spc.spc"),
     "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc"),
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", ""),
+    "d1_dustywave_nonstiff": ("test_files/", "dustywave_nonstiff.par", "hydrogen.spc"),
     "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", ""),
 }
 ARRAYS = ["x_i", "x_i12", "x_iVC", "dx", "surf", "vol", "omegaplus", "omegaminus", "source_pressure_prefactor_left",
