@@ -58,6 +58,13 @@ struct SpeciesConst {           // per-species constants (c_Species + IdealGas_E
     int use_wave;
 };
 
+struct OpaTable {               // one species' .aiopa table (io.cpp:421-566): offsets into DevParams::opa_data
+    int np, nT;
+    int off_p, off_t, off_plog, off_solar, off_planck, off_ross;
+    double inv_mass, mass_amu;
+    int is_dust_like, pad;
+};
+
 struct DevParams {
     // sizes
     int N, N2, NP, S, Bin, Bout, ng, ncol;
@@ -95,6 +102,12 @@ struct DevParams {
     // per-column hydrostatic offsets and gravity source coefficient [ncol][S][NP]
     const double *g_cF, *g_cB, *g_idxF, *g_idxB, *g_wl, *g_wr, *g_ivol, *g_idx;
     double *dpm, *dpp, *gsrc;
+    // per-cell opacities for the models that depend on the local state (T, K, D): [ncol][S][Bin+2*Bout][NP], filled by k_opacity
+    // before the radiation kernel (the reference's update_opacities pass); null for the constant models C and P
+    double *kap_cell;
+    const double *opa_data;             // tabulated opacities of all species, see OpaTable
+    const struct OpaTable *opa_tab;     // [S]
+    double T_star;
     double *Xstore;                     // full FLD: [ncol][N2][n][Bout+1]  X_i = S_i^-1 u_i and S_i^-1 rhs_i (rad_full.cuh)
     double *Tsave, *cssave;             // [ncol][S][NP] prim.temperature / prim.sound_speed as left by the post-hydro
                                         // compute_pressure: friction changes u but not these (source.cpp:485-505), and the

@@ -90,7 +90,7 @@ static void check_supported(const Problem& q) {
     if (q.use_rad_fluxes == 2 && q.num_bands_out != 1) fail("simple FLD solver needs NUM_BANDS_OUT 1");
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && q.num_species > 8) fail("simple FLD + collisional heating with more than 8 species");
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && !q.update_coll_frequently) fail("UPDATE_COLL_FREQUENTLY 0");
-    if (q.use_rad_fluxes && q.opacity_model != 'C' && q.opacity_model != 'P') fail(std::string("opacity model ") + q.opacity_model);
+    if (q.use_rad_fluxes && std::string("CPTKD").find(q.opacity_model) == std::string::npos) fail(std::string("opacity model ") + q.opacity_model);
     if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
     if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
     for (auto& sp : q.species) {
@@ -203,6 +203,29 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     }
     p.sp = im->upload(sc);
     p.kappa_avg = im->upload(kap);
+    // state-dependent opacity models: tables (T, K) and the per-cell opacity array filled by k_opacity every step
+    p.kap_cell = nullptr; p.opa_data = nullptr; p.opa_tab = nullptr; p.T_star = q0.T_star;
+    if (q0.use_rad_fluxes && (q0.opacity_model == 'T' || q0.opacity_model == 'K' || q0.opacity_model == 'D')) {
+        std::vector<double> flat;
+        std::vector<OpaTable> tabs(S);
+        for (int s = 0; s < S; s++) {
+            const SpeciesData& d = q0.species[s];
+            OpaTable& t = tabs[s];
+            memset(&t, 0, sizeof t);
+            t.np = d.opa_pgrid_size; t.nT = d.opa_tgrid_size; t.inv_mass = d.inv_mass; t.mass_amu = d.mass_amu; t.is_dust_like = d.is_dust_like;
+            if (q0.opacity_model != 'D') {
+                if (t.np < 2 || t.nT < 2 || (int)d.opa_grid_planck_log.size() != t.np * t.nT * p.Bout || (int)d.opa_grid_solar_log.size() != t.np * t.nT * p.Bin)
+                    throw std::runtime_error("unsupported configuration: opacity table of species " + d.speciesname + " is missing or malformed");
+                auto put = [&](const std::vector<double>& v) { int off = (int)flat.size(); flat.insert(flat.end(), v.begin(), v.end()); return off; };
+                t.off_p = put(d.opa_pgrid); t.off_t = put(d.opa_tgrid); t.off_plog = put(d.opa_pgrid_log);
+                t.off_solar = put(d.opa_grid_solar_log); t.off_planck = put(d.opa_grid_planck_log); t.off_ross = put(d.opa_grid_rosseland_log);
+            }
+        }
+        if (flat.empty()) flat.push_back(0.);
+        p.opa_data = im->upload(flat);
+        p.opa_tab = im->upload(tabs);
+        p.kap_cell = im->dalloc<double>((size_t)ncol * S * KA * NP);
+    }
 
     // per-column state
     std::vector<double> hu((size_t)3 * ncol * S * NP, 0.0), he((size_t)ncol * S * NP, 0.0), hphi((size_t)ncol * NP, 0.0);
@@ -323,7 +346,8 @@ void Engine::launch_step() {
     mark(1);
     if (im->has_friction) { launch_friction(); im->launches++; }
     mark(2);
-    if (p.use_rad_fluxes == 2 && im->v2 && p.S == 1 && !p.Tsave) {
+    if (p.kap_cell) { AIO_LAUNCH(k_opacity, ncol, 256, 0, im->stream, p); im->launches++; }
+    if (p.use_rad_fluxes == 2 && im->v2 && p.S == 1 && !p.Tsave && !p.kap_cell) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad3<1>, ncol, NT, im->smem_rad3, im->stream, p); break;
         case 2: AIO_LAUNCH(k_rad3<2>, ncol, NT, im->smem_rad3, im->stream, p); break;
@@ -331,7 +355,7 @@ void Engine::launch_step() {
         default: AIO_LAUNCH(k_rad3<8>, ncol, NT, im->smem_rad3, im->stream, p); break;
         }
         im->launches++;
-    } else if (p.use_rad_fluxes == 2 && im->v2 && !(p.use_collisional_heating && p.S > 1)) {
+    } else if (p.use_rad_fluxes == 2 && im->v2 && !(p.use_collisional_heating && p.S > 1) && !p.kap_cell) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_rad2<1>, ncol, NT, im->smem_rad2, im->stream, p); break;
         case 2: AIO_LAUNCH(k_rad2<2>, ncol, NT, im->smem_rad2, im->stream, p); break;

@@ -212,8 +212,42 @@ void read_species_data(Sim& S, Spec& s, const std::string& filename, int species
     d.static_charge = (std::abs(temp_static_charge) < 0.1) ? 0 : std::floor(temp_static_charge);
 
     const char om = q.opacity_model;
-    if (om == 'T' || om == 'K') throw std::runtime_error("unsupported configuration: tabulated opacities (PARI_OPACITY_MODEL T/K)");
-    if (!(om == 'P' || om == 'M' || om == 'C')) return;
+    if (om == 'T' || om == 'K') {                  // read_opacity_table, io.cpp:421-566
+        const std::string tpath = "inputdata/" + s.opacity_data_string;
+        std::ifstream tf(tpath);
+        if (!tf) throw std::runtime_error("cannot open opacity table " + tpath);
+        auto next_tokens = [&]() { std::string l; if (!std::getline(tf, l)) throw std::runtime_error("opacity table " + tpath + " ends early"); return stringsplit(l, " "); };
+        auto t = next_tokens();
+        if (t.size() < 2) throw std::runtime_error("malformed header in " + tpath);
+        const int np = (int)std::stod(t[0]), nT = (int)std::stod(t[1]);
+        if (np <= 0 || nT <= 0 || np > 9999 || nT > 9999) throw std::runtime_error("bad grid size in " + tpath);
+        d.opa_pgrid_size = np; d.opa_tgrid_size = nT;
+        d.opa_pgrid.assign(np, 0.); d.opa_tgrid.assign(nT, 0.); d.opa_pgrid_log.assign(np, 0.); d.opa_tgrid_log.assign(nT, 0.);
+        d.opa_grid_solar_log.assign((size_t)np * nT * q.num_bands_in, 0.);
+        d.opa_grid_planck_log.assign((size_t)np * nT * q.num_bands_out, 0.);
+        d.opa_grid_rosseland_log.assign((size_t)np * nT * q.num_bands_out, 0.);
+        next_tokens();                               // one empty line
+        t = next_tokens();
+        if ((int)t.size() < np) throw std::runtime_error("short pressure grid in " + tpath);
+        for (int i = 0; i < np; i++) { d.opa_pgrid[i] = std::stod(t[i]); d.opa_pgrid_log[i] = std::log10(d.opa_pgrid[i]); }
+        t = next_tokens();
+        if ((int)t.size() < nT) throw std::runtime_error("short temperature grid in " + tpath);
+        for (int i = 0; i < nT; i++) { d.opa_tgrid[i] = std::stod(t[i]); d.opa_tgrid_log[i] = std::log10(d.opa_tgrid[i]); }
+        auto read_blocks = [&](std::vector<double>& dst, int nb) {
+            next_tokens();                           // header line of the block group
+            for (int b = 0; b < nb; b++)
+                for (int i = 0; i < np; i++) {
+                    auto r = next_tokens();
+                    if ((int)r.size() < nT) throw std::runtime_error("short opacity row in " + tpath);
+                    for (int j = 0; j < nT; j++) dst[(size_t)j + (size_t)i * nT + (size_t)b * np * nT] = std::log10(std::stod(r[j]));
+                }
+        };
+        read_blocks(d.opa_grid_solar_log, 1);        // only the first incoming band is read (io.cpp:503)
+        read_blocks(d.opa_grid_planck_log, q.num_bands_out);
+        read_blocks(d.opa_grid_rosseland_log, q.num_bands_out);
+    }
+    if (!(om == 'P' || om == 'M' || om == 'C' || om == 'K')) return;
+    if (om == 'K') s.opacity_data_string = s.opacity_corrk_string;
     const std::string path = "inputdata/" + s.opacity_data_string;
     // The band means depend on the file, the band edges and PARI_CONST_OPAC only: columns of a sweep share them, and the
     // re-gridding below walks ~1e5 points per file, so the result is cached per process.

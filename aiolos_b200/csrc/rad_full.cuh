@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
             const double dxj = __ldg(p.dx + j);
             if (b < Bin) {
                 double tot = 0;
-                for (int s = 0; s < S; s++) tot += kap[s * KA + b] * p.u[idx_u(p, 0, col, s, j)];
+                for (int s = 0; s < S; s++) tot += kapv(p, col, s, b, j) * p.u[idx_u(p, 0, col, s, j)];
                 const double cell_tau = tot * dxj;
                 const double rad_j = (j == N + 1) ? 0. : rad_above + cell_tau;
                 double dSb;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
                 if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
                 for (int s = 0; s < S; s++) {
                     const double hsw = p.highenergy_switch[s * Bin + b];
-                    const double frac = hsw * kap[s * KA + b] * p.u[idx_u(p, 0, col, s, j)] * dxj / cell_tau;
+                    const double frac = hsw * kapv(p, col, s, b, j) * p.u[idx_u(p, 0, col, s, j)] * dxj / cell_tau;
                     contrib[s * Bin + b] = hsw * dSb * frac;
                 }
                 rad_above = rad_j;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
     auto total_opacity = [&](int j, int b) -> double {
         if (j < 1 || j > N + 1) return 0.;
         double tot = 0;
-        for (int s = 0; s < S; s++) tot = fmax(kap[s * KA + Bin + Bout + b] * p.u[idx_u(p, 0, col, s, j)], tot);
+        for (int s = 0; s < S; s++) tot = fmax(kapv(p, col, s, Bin + Bout + b, j) * p.u[idx_u(p, 0, col, s, j)], tot);
         return tot;
     };
     if (isJ) to_ip = total_opacity(0, lane);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
                 const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
                 Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
                 const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
-                facs[s * Bout + lane] = 1. * p.no_rad_trans * kap[s * KA + Bin + lane] * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
+                facs[s * Bout + lane] = 1. * p.no_rad_trans * kapv(p, col, s, Bin + lane, i) * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
                                         planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts);
             }
         }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
                     Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
                     const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
                     const double fac = facs[s * Bout + b];
-                    d += vj * q.rho * kap[s * KA + Bin + b] * p.no_rad_trans;
+                    d += vj * q.rho * kapv(p, col, s, Bin + b, i) * p.no_rad_trans;
                     A[b * LD + Bout + s] = -4 * vj * q.rho * fac;
                     rhs -= 3 * vj * q.rho * fac * Ts;
                 }
@@ -228,14 +228,14 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
             for (int b = 0; b < Bout; b++) {
                 const double fac = facs[s * Bout + b];
                 d += 16 * C_PI * fac / sc.cv;
-                A[lane * LD + b] = -4 * C_PI * kap[s * KA + Bin + b] * p.no_rad_trans / sc.cv;
+                A[lane * LD + b] = -4 * C_PI * kapv(p, col, s, Bin + b, i) * p.no_rad_trans / sc.cv;
                 rhs += 12 * C_PI * fac * Ts / sc.cv;
             }
             A[lane * LD + lane] = d;
             // collisional T_i - T_j coupling (radiation.cpp:589-615, source.cpp:656-674)
             if (p.use_collisional_heating && S > 1) {
                 double tot0 = 0;
-                if (i >= 1) for (int ss = 0; ss < S; ss++) tot0 = fmax(kap[ss * KA + Bin + Bout + 0] * p.u[idx_u(p, 0, col, ss, i)], tot0);
+                if (i >= 1) for (int ss = 0; ss < S; ss++) tot0 = fmax(kapv(p, col, ss, Bin + Bout + 0, i) * p.u[idx_u(p, 0, col, ss, i)], tot0);
                 const double tau = tot0 * (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
                 const double damp = (tau < 1e3) ? 1. : 1.e-4;
                 double diag_sum = 0, self = 0;

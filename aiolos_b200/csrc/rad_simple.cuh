@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "hydro.cuh"
 #include "friction.cuh"
+#include "opacity.cuh"
 
 namespace aio {
 
@@ -135,7 +136,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
         for (int q = tid; q < N; q += NT) {
             const int j = N - q;
             double tot = 0;
-            for (int s = 0; s < S; s++) tot += p.kappa_avg[s * KA + b] * RHO[s * N2 + j];
+            for (int s = 0; s < S; s++) tot += kapv(p, col, s, b, j) * RHO[s * N2 + j];
             TAU[q] = tot * __ldg(p.dx + j);
         }
         __syncthreads();
@@ -143,7 +144,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
         for (int j = tid + 1; j <= N + 1; j += NT) {
             const double dxj = __ldg(p.dx + j);
             double tot = 0;
-            for (int s = 0; s < S; s++) tot += p.kappa_avg[s * KA + b] * RHO[s * N2 + j];
+            for (int s = 0; s < S; s++) tot += kapv(p, col, s, b, j) * RHO[s * N2 + j];
             const double cell_tau = tot * dxj;
             double dSb;
             if (j < N + 1) {
@@ -164,7 +165,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
             if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
             for (int s = 0; s < S; s++) {
                 const double hsw = p.highenergy_switch[s * Bin + b];
-                const double frac = hsw * p.kappa_avg[s * KA + b] * RHO[s * N2 + j] * dxj / cell_tau;
+                const double frac = hsw * kapv(p, col, s, b, j) * RHO[s * N2 + j] * dxj / cell_tau;
                 double v = DS[s * N2 + j] + hsw * dSb * frac;
                 if (v < 1e-50) v = 0.;
                 DS[s * N2 + j] = v;
@@ -176,7 +177,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
     // ---- thermal band: total opacity (max over species, radiation.cpp:77) -------------------------------------------------
     for (int j = tid; j < N2; j += NT) {
         double tot = 0;
-        if (j >= 1) for (int s = 0; s < S; s++) tot = fmax(p.kappa_avg[s * KA + Bin + p.Bout + 0] * RHO[s * N2 + j], tot);
+        if (j >= 1) for (int s = 0; s < S; s++) tot = fmax(kapv(p, col, s, Bin + p.Bout + 0, j) * RHO[s * N2 + j], tot);
         // cell 0 is never updated by update_dS (loop j>0) and keeps its initial 0; it is not read by the solver either
         TO[j] = tot;
     }
@@ -216,7 +217,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
             for (int s = 0; s < S; s++) {
                 const SpeciesConst sc = p.sp[s];
                 const double Ts = TT[s * N2 + j], Ts3 = Ts * Ts * Ts, rhos = RHO[s * N2 + j];
-                const double kappa = p.kappa_avg[s * KA + Bin + 0];
+                const double kappa = kapv(p, col, s, Bin + 0, j);
                 const double fac = 1. * ddt * p.no_rad_trans * kappa / sc.cv * C_SIGMA_RAD * Ts3;
                 const double u1 = rhos;
                 const double moredenom = -p.photocooling_expansion * 0. * ddt / (sc.cv * u1);
@@ -283,7 +284,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
                 b[si] = 0.;
                 if (si < S) {
                     const SpeciesConst ci = p.sp[si];
-                    const double kappa = p.kappa_avg[si * KA + Bin + 0];
+                    const double kappa = kapv(p, col, si, Bin + 0, j);
                     const double eta2 = 4. * C_PI * ddt * kappa * p.no_rad_trans / ci.cv;
                     M[si][si] += DEN[si * N2 + j];
                     if (p.couple_J_into_T) b[si] += eta2 * JJ[j];
@@ -339,7 +340,7 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
             double T = TT[s * N2 + j];
             if (collheat) { if (j <= N) T = Tcoll[s]; }
             else if (j <= N && p.radiation_matter_equilibrium_test <= 2) {
-                const double kappa = p.kappa_avg[s * KA + Bin + 0];
+                const double kappa = kapv(p, col, s, Bin + 0, j);
                 const double eta2 = 4. * C_PI * ddt * kappa * p.no_rad_trans / sc.cv;
                 double tt = E1[s * N2 + j] / DEN[s * N2 + j];
                 if (p.couple_J_into_T) tt += eta2 / DEN[s * N2 + j] * JJ[j];

@@ -38,6 +38,8 @@ CASES = {
     "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", None, [1, 100, 1000]),
     # the same with the full FLD solver: 3x3 blocks (J, T_1, T_2) with the collisional T-T coupling of radiation.cpp:589-615
     "c6_dynamic3_2spc_fullfld": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_fullfld.par", None, [1, 100, 1000]),
+    # configs[3] with PARI_OPACITY_MODEL T and a reference .aiopa table (our variant): tabulated kappa(p, T) interpolation
+    "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", None, [1, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
 }

@@ -18,6 +18,7 @@ DECKS = {   # case -> (deck dir, par, spc)
     "c3_searth_22b": ("test2/", "SEarth_opacities_1s22b.par", "irradiation.spc"),
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", ""),
     "d1_dustywave_nonstiff": ("test_files/", "dustywave_nonstiff.par", "hydrogen.spc"),
+    "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", ""),
     "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", ""),
 }
 ARRAYS = ["x_i", "x_i12", "x_iVC", "dx", "surf", "vol", "omegaplus", "omegaminus", "source_pressure_prefactor_left",
@@ -70,7 +71,7 @@ def test_constructor_state(emu_lib, rundir, case, monkeypatch):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("case,k", [("c1_planet_spherical", 100), ("c4_dynamic3_euv", 100), ("c2m_friction_6spc_mild", 100),
+@pytest.mark.parametrize("case,k", [("c1_planet_spherical", 100), ("c4_dynamic3_euv", 100), ("c7_dynamic3_tabulated", 100), ("c2m_friction_6spc_mild", 100),
                                     ("c3_searth_22b", 20)])
 def test_files_to_k_steps(emu_lib, rundir, case, k, monkeypatch):
     monkeypatch.chdir(rundir)

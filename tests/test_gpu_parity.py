@@ -18,6 +18,7 @@ CASES = [
     ("c5_dynamic3_2spc_collheat", 1, 1e-10), ("c5_dynamic3_2spc_collheat", 100, 1e-8), ("c5_dynamic3_2spc_collheat", 1000, 1e-8),
     ("c6_dynamic3_2spc_fullfld", 1, 1e-10), ("c6_dynamic3_2spc_fullfld", 100, 1e-8), ("c6_dynamic3_2spc_fullfld", 1000, 1e-8),
     ("d1_dustywave_nonstiff", 1, 1e-10), ("d1_dustywave_nonstiff", 100, 1e-8), ("d1_dustywave_nonstiff", 800, 1e-8),
+    ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8), ("c7_dynamic3_tabulated", 1000, 1e-8),
 ]
 
 
