@@ -115,6 +115,7 @@ struct DevParams {
     double *prim2v;                     // [ncol][S]  prim[2].speed as last computed (fixed BC, init_and_bounds.cpp:1856)
     const double *solar_heating_final;  // [ncol][Bin]
     ColState* cs;                       // [ncol]
+    int steps_per_launch;               // fused persistent kernel (k_step1): time steps one launch may advance a column
     long long step_limit;               // columns stop when steps reaches this
 };
 

@@ -29,7 +29,9 @@ struct Engine::Impl {
     int nt_full = 0; size_t smem_full = 0;
     bool has_friction = false;
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
-    size_t smem_rad2 = 0, smem_rad3 = 0;
+    size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
+    bool fused = false;             // single-species persistent step kernel (k_step1)
+    int steps_per_launch = 16;
     long long launches = 0;
     std::vector<ColState> h_cs;
     double* pinned = nullptr; size_t pinned_bytes = 0;
@@ -284,12 +286,15 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_rad = ((size_t)(5 * S + 7) * N2 + 32) * sizeof(double);
     im->smem_fric = 64 * sizeof(double);
     im->smem_rad2 = ((size_t)(5 * S + 7) * N2 + 32 + 4 * NT) * sizeof(double);
-    im->smem_rad3 = ((size_t)7 * N2 + 32 + 4 * NT) * sizeof(double);
+    im->smem_rad3 = ((size_t)7 * NT * CPT + 32 + 4 * NT) * sizeof(double);
+    im->smem_step1 = std::max(im->smem_hydro, p.use_rad_fluxes == 2 ? im->smem_rad3 : (size_t)0) + 64 * sizeof(double);
+    im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
         throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
 #define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
     SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
+    SETSM(k_step1<1>, im->smem_step1); SETSM(k_step1<2>, im->smem_step1); SETSM(k_step1<4>, im->smem_step1); SETSM(k_step1<8>, im->smem_step1);
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
         if (im->smem_rad2 > (size_t)maxsm) throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
@@ -385,12 +390,39 @@ void Engine::kernel_times(long long nsteps, double* out3) {
     if (!im->prof_ev[0]) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&im->prof_ev[k]));
     for (int k = 0; k < 3; k++) im->prof_ms[k] = 0;
     im->p.step_limit += nsteps;
+    if (im->fused && im->v2) {          // one kernel does the whole step: report it in slot 0
+        CK(cudaEventRecord(im->prof_ev[0], im->stream));
+        launch_fused(nsteps);
+        CK(cudaEventRecord(im->prof_ev[1], im->stream));
+        CK(cudaEventSynchronize(im->prof_ev[1]));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, im->prof_ev[0], im->prof_ev[1]));
+        out3[0] = ms / (double)nsteps; out3[1] = 0; out3[2] = 0;
+        return;
+    }
     im->prof_on = true;
     for (long long k = 0; k < nsteps; k++) launch_step();
     im->prof_on = false;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(im->stream));
     for (int k = 0; k < 3; k++) out3[k] = nsteps > 0 ? im->prof_ms[k] / (double)nsteps : 0.0;
+}
+
+// Single-species decks: one launch of the persistent kernel advances every column by up to steps_per_launch steps.
+void Engine::launch_fused(long long nsteps) {
+    DevParams& p = im->p;
+    const int ncol = p.ncol, NT = im->NT;
+    long long left = nsteps;
+    while (left > 0) {
+        p.steps_per_launch = (int)std::min<long long>(left, im->steps_per_launch);
+        switch (im->CPT) {
+        case 1: AIO_LAUNCH(k_step1<1>, ncol, NT, im->smem_step1, im->stream, p); break;
+        case 2: AIO_LAUNCH(k_step1<2>, ncol, NT, im->smem_step1, im->stream, p); break;
+        case 4: AIO_LAUNCH(k_step1<4>, ncol, NT, im->smem_step1, im->stream, p); break;
+        default: AIO_LAUNCH(k_step1<8>, ncol, NT, im->smem_step1, im->stream, p); break;
+        }
+        im->launches++;
+        left -= p.steps_per_launch;
+    }
 }
 
 // Advance every column by up to `nsteps` further steps (columns that reach their t_max or crash stop earlier).
@@ -400,7 +432,8 @@ double Engine::advance(long long nsteps, bool timed) {
                                 // desynchronise the ensemble; a global ceiling keeps "advance(k)" = k steps for all
     // step_limit is an absolute ceiling on ColState.steps
     if (timed) CK(cudaEventRecord(im->ev0, im->stream));
-    for (long long k = 0; k < nsteps; k++) launch_step();
+    if (im->fused && im->v2) launch_fused(nsteps);
+    else for (long long k = 0; k < nsteps; k++) launch_step();
     CK(cudaGetLastError());
     float ms = 0;
     if (timed) { CK(cudaEventRecord(im->ev1, im->stream)); CK(cudaEventSynchronize(im->ev1)); CK(cudaEventElapsedTime(&ms, im->ev0, im->ev1)); }
@@ -445,6 +478,13 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         if (value == "thomas") im->p.tridiag_serial = 1;
         else if (value == "pcr") im->p.tridiag_serial = 0;
         else throw std::invalid_argument("option tridiag: expected 'pcr' or 'thomas'");
+    } else if (key == "steps_per_launch") {
+        const int k = atoi(value.c_str());
+        if (k < 1 || k > 100000) throw std::invalid_argument("option steps_per_launch: expected 1..100000");
+        im->steps_per_launch = k;
+    } else if (key == "fused") {
+        if (value == "0") im->fused = false;
+        else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");
     } else if (key == "kernels") {
         if (value == "v1") im->v2 = false;
         else if (value == "v2") im->v2 = true;

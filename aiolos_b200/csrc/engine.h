@@ -38,6 +38,7 @@ private:
     Impl* im;
     Problem prob0;
     void launch_step();
+    void launch_fused(long long nsteps);
     void launch_friction();
     void launch_full();
     void full_setup();

@@ -237,17 +237,19 @@ __device__ __forceinline__ void tail_cell(const DevParams& p, int col, int s, in
     if (j <= p.N) p.eint[k] = eint;
 }
 
-__device__ inline void tail_commit(const DevParams& p, int col, TailAcc a, double* red, bool negJ = false, double Jval = 0) {
+__device__ inline void tail_commit_on(ColState& c, TailAcc a, double* red, bool negJ = false, double Jval = 0) {
     double ms = block_max(a.minstep, red);
     double md = block_max(a.maxde, red);
     int bad = block_or(a.bad);
     if (threadIdx.x == 0) {
-        ColState& c = p.cs[col];
         c.minstep = ms; c.maxde = md;
         c.steps += 1;
         if (bad) { c.status = COL_NEG_T; c.t = 1.1 * c.t_max; }
         else if (negJ) { c.status = COL_NEG_J; c.crash_value = Jval; c.t = 1.1 * c.t_max; }
     }
+}
+__device__ inline void tail_commit(const DevParams& p, int col, TailAcc a, double* red, bool negJ = false, double Jval = 0) {
+    tail_commit_on(p.cs[col], a, red, negJ, Jval);
 }
 
 // One column, one time step of hydrodynamics for all species.  `sm` = dynamic shared memory of the CTA
@@ -421,12 +423,11 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
 // Step head for one column (thread 0 decides, everybody learns through shared memory): is the column still running,
 // and with which dt (advection.cpp:60-77).  Returns 0 when the column is finished / crashed / at its step ceiling.
 struct StepInfo { double dt, t_old; int active, snap; };
-__device__ __forceinline__ StepInfo step_head(const DevParams& p, const int col) {
+__device__ __forceinline__ StepInfo step_head_on(const DevParams& p, ColState& c) {
     __shared__ double s_dt, s_t;
     __shared__ int s_active, s_snap;
     __syncthreads();
     if (threadIdx.x == 0) {
-        ColState& c = p.cs[col];
         int active = (c.status == COL_OK) && (c.t < c.t_max) && (c.steps < p.step_limit);
         s_active = active;
         c.in_step = active;
@@ -442,6 +443,7 @@ __device__ __forceinline__ StepInfo step_head(const DevParams& p, const int col)
     if (si.active) { si.dt = s_dt; si.t_old = s_t; si.snap = s_snap; }
     return si;
 }
+__device__ __forceinline__ StepInfo step_head(const DevParams& p, const int col) { return step_head_on(p, p.cs[col]); }
 
 template <int CPT>
 __global__ void __launch_bounds__(256, 2) k_hydro(DevParams p) {

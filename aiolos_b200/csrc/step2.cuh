@@ -121,6 +121,142 @@ __device__ __forceinline__ void hllc_flux2(double dl, double ul, double pl, doub
     f1 = r1; f2 = r2; f3 = r3;
 }
 
+// Both Heun stages of one species on register-resident cells (u1,u2,u3 of the cells this thread owns); `sm` as in hydro_phase_v2.
+template <int CPT>
+__device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int col, const int s, const SpeciesConst& sc, double* sm,
+                                                const double dt, const double t_old, double (&u1)[CPT], double (&u2)[CPT],
+                                                double (&u3)[CPT], double& prim2_speed) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = p.N, N2 = p.N2, ng = p.ng;
+    double* Pr = sm;            double* Pv = Pr + N2;  double* Pp = Pv + N2;
+    double* Lr = Pp + N2;       double* Lv = Lr + N2;  double* Lp = Lv + N2;
+    double* Rr = Lp + N2;       double* Rv = Rr + N2;  double* Rp = Rv + N2;
+    double* win = Rp + N2 + 32;
+    BndWin W; W.w = win; W.ng = ng; W.N2 = N2;
+    const bool second = (p.order == 2);
+    const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1;
+    const bool is_gas = !sc.is_dust_like;
+    const double* __restrict__ DPM = p.dpm + idx_s(p, col, s, 0);
+    const double* __restrict__ DPP = p.dpp + idx_s(p, col, s, 0);
+    const double* __restrict__ GS = p.gsrc + idx_s(p, col, s, 0);
+    double d1[CPT], d2[CPT], d3[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) d1[k] = d2[k] = d3[k] = 0;
+    const int nstage = second ? 2 : 1;
+    for (int stage = 0; stage < nstage; stage++) {
+        // ---- boundary conditions (init_and_bounds.cpp:1779-1987) on the 2*ng cells next to each end ------------------------
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < N2 && (j < 2 * ng || j >= N2 - 2 * ng)) { W.at(0, j) = u1[k]; W.at(1, j) = u2[k]; W.at(2, j) = u3[k]; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            apply_boundary_left(p, sc, col, s, W, prim2_speed);
+            if (sc.use_wave == 1) {
+                const double tt = (stage == 0) ? t_old : t_old + dt;
+                W.at(1, 0) = W.at(0, 0) * sc.wave_amplitude * sin(12. * M_PI * tt / sc.wave_period);
+                W.at(1, 1) = W.at(1, 0);
+            }
+        }
+        if (tid == ((NT > 32) ? 32 : 0)) apply_boundary_right(p, sc, col, s, W);
+        __syncthreads();
+        // ---- cons -> prim (eos.cpp:19-29) --------------------------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < N2) {
+                if (j < 2 * ng || j >= N2 - 2 * ng) { u1[k] = W.at(0, j); u2[k] = W.at(1, j); u3[k] = W.at(2, j); }
+                const double v = u2[k] * frcp(u1[k]);
+                Pr[j] = u1[k]; Pv[j] = v; Pp[j] = gm1 * (u3[k] - 0.5 * u2[k] * v);
+            }
+        }
+        __syncthreads();
+        prim2_speed = Pv[2 < N2 ? 2 : 0];
+        // ---- well-balanced reconstruction (reconstruct.cpp:34-117) ----------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int i = tid + k * NT;
+            if (i < N2) {
+                const double rho = Pr[i], v = Pv[i], pr0 = Pp[i];
+                double lr = rho, lv = v, lp = pr0, rr = rho, rv = v, rp = pr0;
+                double dpm = 0, dpp = 0;
+                if (is_gas) {
+                    dpm = __ldg(DPM + i); dpp = __ldg(DPP + i);
+                    if (i > 0) lp = pr0 + rho * dpm;
+                    if (i <= N) rp = pr0 + rho * dpp;
+                    if (lp < 0 || rp < 0) { lp = pr0; rp = pr0; }
+                }
+                if (second && i >= 1 && i <= N) {
+                    const double rhom = Pr[i - 1], rhop = Pr[i + 1];
+                    double dp_l = 0, dp_r = 0;
+                    if (is_gas) {
+                        dp_l = rho * dpm - rhom * __ldg(DPP + i - 1);
+                        dp_r = rho * dpp - rhop * __ldg(DPM + i + 1);
+                    }
+                    const double cF = __ldg(p.g_cF + i), cB = __ldg(p.g_cB + i), ixF = __ldg(p.g_idxF + i), ixB = __ldg(p.g_idxB + i);
+                    const double wl = __ldg(p.g_wl + i), wr = __ldg(p.g_wr + i);
+                    double slope = mc_slope2(Pp[i - 1] - dp_l, pr0, Pp[i + 1] - dp_r, cF, cB, ixF, ixB);
+                    lp += slope * wl; rp += slope * wr;
+                    slope = mc_slope2(rhom, rho, rhop, cF, cB, ixF, ixB);
+                    lr += slope * wl; rr += slope * wr;
+                    slope = mc_slope2(Pv[i - 1], v, Pv[i + 1], cF, cB, ixF, ixB);
+                    lv += slope * wl; rv += slope * wr;
+                    if ((lp < 0) || (rp < 0) || (lr < 0) || (rr < 0)) { lr = rr = rho; lv = rv = v; lp = rp = pr0; }
+                }
+                Lr[i] = lr; Lv[i] = lv; Lp[i] = lp; Rr[i] = rr; Rv[i] = rv; Rp[i] = rp;
+            }
+        }
+        __syncthreads();
+        // ---- interface fluxes, stored over the (now dead) cell prims ---------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j <= N) {
+                double f1, f2, f3;
+                if (is_gas) hllc_flux2(Rr[j], Rv[j], Rp[j], Lr[j + 1], Lv[j + 1], Lp[j + 1], gm1, igm1, f1, f2, f3);
+                else dust_flux(Rr[j], Rv[j], Rp[j], Lr[j + 1], Lv[j + 1], Lp[j + 1], gm1, f1, f2, f3);
+                Pr[j] = f1; Pv[j] = f2; Pp[j] = f3;
+            }
+        }
+        __syncthreads();
+        // ---- sources, dudt, update (source.cpp:157-164, advection.cpp:492-503, 154-158, 187-195) ---------------------------------------
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            double t1 = 0, t2 = 0, t3 = 0;
+            if (j >= 1 && j <= N) {
+                const double g = __ldg(GS + j);
+                const double s2 = (u1[k] * (-1.)) * g, s3 = (u2[k] * (-1.)) * g;
+                const double sp2 = -(__ldg(p.spp_left + j) * Lp[j] - __ldg(p.spp_right + j) * Rp[j]);
+                const double sl = __ldg(p.surf + j - 1), sr = __ldg(p.surf + j), iv = __ldg(p.g_ivol + j);
+                t1 = (Pr[j - 1] * sl - Pr[j] * sr) * iv;
+                t2 = (Pv[j - 1] * sl - Pv[j] * sr) * iv + (s2 + sp2);
+                t3 = (Pp[j - 1] * sl - Pp[j] * sr) * iv + s3;
+            }
+            if (stage == 0) {
+                d1[k] = t1; d2[k] = t2; d3[k] = t3;
+                u1[k] = u1[k] + t1 * dt; u2[k] = u2[k] + t2 * dt; u3[k] = u3[k] + t3 * dt;
+            } else {
+                u1[k] += (t1 - d1[k]) * dt * 0.5; u2[k] += (t2 - d2[k]) * dt * 0.5; u3[k] += (t3 - d3[k]) * dt * 0.5;
+            }
+        }
+    }
+}
+
+// phi_s snapshot + static tables (first two steps only, see hydro.cuh)
+__device__ inline void hydro_snapshot_v2(const DevParams& p, const int col) {
+    const int tid = threadIdx.x, NT = blockDim.x, N2 = p.N2;
+    const double* phi = p.phi + idx_c(p, col, 0);
+    for (int s = 0; s < p.S; s++) {
+        double* phis = p.phis + idx_s(p, col, s, 0);
+        for (int j = tid; j < N2; j += NT) phis[j] = phi[j] * 1.0;
+    }
+    __syncthreads();
+    build_static_tables(p, col);
+    __syncthreads();
+}
+
 template <int CPT>
 __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col, double* sm, const double dt, const double t_old,
                                                const int snap, TailAcc& acc) {
@@ -153,115 +289,15 @@ __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col
         const double* __restrict__ DPM = p.dpm + idx_s(p, col, s, 0);
         const double* __restrict__ DPP = p.dpp + idx_s(p, col, s, 0);
         const double* __restrict__ GS = p.gsrc + idx_s(p, col, s, 0);
-        double u1[CPT], u2[CPT], u3[CPT], d1[CPT], d2[CPT], d3[CPT];
+        double u1[CPT], u2[CPT], u3[CPT];
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int j = tid + k * NT;
             if (j < N2) { u1[k] = U1[j]; u2[k] = U2[j]; u3[k] = U3[j]; }
             else { u1[k] = 1; u2[k] = 0; u3[k] = 1; }
-            d1[k] = d2[k] = d3[k] = 0;
         }
         double prim2_speed = p.prim2v[(size_t)col * p.S + s];
-        const int nstage = second ? 2 : 1;
-        for (int stage = 0; stage < nstage; stage++) {
-            // ---- boundary conditions (init_and_bounds.cpp:1779-1987) on the 2*ng cells next to each end ------------------------
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const int j = tid + k * NT;
-                if (j < N2 && (j < 2 * ng || j >= N2 - 2 * ng)) { W.at(0, j) = u1[k]; W.at(1, j) = u2[k]; W.at(2, j) = u3[k]; }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                apply_boundary_left(p, sc, col, s, W, prim2_speed);
-                if (sc.use_wave == 1) {
-                    const double tt = (stage == 0) ? t_old : t_old + dt;
-                    W.at(1, 0) = W.at(0, 0) * sc.wave_amplitude * sin(12. * M_PI * tt / sc.wave_period);
-                    W.at(1, 1) = W.at(1, 0);
-                }
-            }
-            if (tid == ((NT > 32) ? 32 : 0)) apply_boundary_right(p, sc, col, s, W);
-            __syncthreads();
-            // ---- cons -> prim (eos.cpp:19-29) --------------------------------------------------------------------------------------
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const int j = tid + k * NT;
-                if (j < N2) {
-                    if (j < 2 * ng || j >= N2 - 2 * ng) { u1[k] = W.at(0, j); u2[k] = W.at(1, j); u3[k] = W.at(2, j); }
-                    const double v = u2[k] * frcp(u1[k]);
-                    Pr[j] = u1[k]; Pv[j] = v; Pp[j] = gm1 * (u3[k] - 0.5 * u2[k] * v);
-                }
-            }
-            __syncthreads();
-            prim2_speed = Pv[2 < N2 ? 2 : 0];
-            // ---- well-balanced reconstruction (reconstruct.cpp:34-117) ----------------------------------------------------------------
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const int i = tid + k * NT;
-                if (i < N2) {
-                    const double rho = Pr[i], v = Pv[i], pr0 = Pp[i];
-                    double lr = rho, lv = v, lp = pr0, rr = rho, rv = v, rp = pr0;
-                    double dpm = 0, dpp = 0;
-                    if (is_gas) {
-                        dpm = __ldg(DPM + i); dpp = __ldg(DPP + i);
-                        if (i > 0) lp = pr0 + rho * dpm;
-                        if (i <= N) rp = pr0 + rho * dpp;
-                        if (lp < 0 || rp < 0) { lp = pr0; rp = pr0; }
-                    }
-                    if (second && i >= 1 && i <= N) {
-                        const double rhom = Pr[i - 1], rhop = Pr[i + 1];
-                        double dp_l = 0, dp_r = 0;
-                        if (is_gas) {
-                            dp_l = rho * dpm - rhom * __ldg(DPP + i - 1);
-                            dp_r = rho * dpp - rhop * __ldg(DPM + i + 1);
-                        }
-                        const double cF = __ldg(p.g_cF + i), cB = __ldg(p.g_cB + i), ixF = __ldg(p.g_idxF + i), ixB = __ldg(p.g_idxB + i);
-                        const double wl = __ldg(p.g_wl + i), wr = __ldg(p.g_wr + i);
-                        double slope = mc_slope2(Pp[i - 1] - dp_l, pr0, Pp[i + 1] - dp_r, cF, cB, ixF, ixB);
-                        lp += slope * wl; rp += slope * wr;
-                        slope = mc_slope2(rhom, rho, rhop, cF, cB, ixF, ixB);
-                        lr += slope * wl; rr += slope * wr;
-                        slope = mc_slope2(Pv[i - 1], v, Pv[i + 1], cF, cB, ixF, ixB);
-                        lv += slope * wl; rv += slope * wr;
-                        if ((lp < 0) || (rp < 0) || (lr < 0) || (rr < 0)) { lr = rr = rho; lv = rv = v; lp = rp = pr0; }
-                    }
-                    Lr[i] = lr; Lv[i] = lv; Lp[i] = lp; Rr[i] = rr; Rv[i] = rv; Rp[i] = rp;
-                }
-            }
-            __syncthreads();
-            // ---- interface fluxes, stored over the (now dead) cell prims ---------------------------------------------------------------
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const int j = tid + k * NT;
-                if (j <= N) {
-                    double f1, f2, f3;
-                    if (is_gas) hllc_flux2(Rr[j], Rv[j], Rp[j], Lr[j + 1], Lv[j + 1], Lp[j + 1], gm1, igm1, f1, f2, f3);
-                    else dust_flux(Rr[j], Rv[j], Rp[j], Lr[j + 1], Lv[j + 1], Lp[j + 1], gm1, f1, f2, f3);
-                    Pr[j] = f1; Pv[j] = f2; Pp[j] = f3;
-                }
-            }
-            __syncthreads();
-            // ---- sources, dudt, update (source.cpp:157-164, advection.cpp:492-503, 154-158, 187-195) ---------------------------------------
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const int j = tid + k * NT;
-                double t1 = 0, t2 = 0, t3 = 0;
-                if (j >= 1 && j <= N) {
-                    const double g = __ldg(GS + j);
-                    const double s2 = (u1[k] * (-1.)) * g, s3 = (u2[k] * (-1.)) * g;
-                    const double sp2 = -(__ldg(p.spp_left + j) * Lp[j] - __ldg(p.spp_right + j) * Rp[j]);
-                    const double sl = __ldg(p.surf + j - 1), sr = __ldg(p.surf + j), iv = __ldg(p.g_ivol + j);
-                    t1 = (Pr[j - 1] * sl - Pr[j] * sr) * iv;
-                    t2 = (Pv[j - 1] * sl - Pv[j] * sr) * iv + (s2 + sp2);
-                    t3 = (Pp[j - 1] * sl - Pp[j] * sr) * iv + s3;
-                }
-                if (stage == 0) {
-                    d1[k] = t1; d2[k] = t2; d3[k] = t3;
-                    u1[k] = u1[k] + t1 * dt; u2[k] = u2[k] + t2 * dt; u3[k] = u3[k] + t3 * dt;
-                } else {
-                    u1[k] += (t1 - d1[k]) * dt * 0.5; u2[k] += (t2 - d2[k]) * dt * 0.5; u3[k] += (t3 - d3[k]) * dt * 0.5;
-                }
-            }
-        }
+        hydro_stages_v2<CPT>(p, col, s, sc, sm, dt, t_old, u1, u2, u3, prim2_speed);
         // ---- write back; final compute_pressure (advection.cpp:204-205) and tail ---------------------------------------------------------
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -296,18 +332,69 @@ __global__ void __launch_bounds__(256, AIO_HYDRO2_MINB) k_hydro2(DevParams p) {
     if (p.last_kernel == 0) tail_commit(p, col, acc, sm + 9 * p.N2);
 }
 
+// ---- chunked shared-memory access: thread t owns elements [t*M, t*M+M); 16-byte accesses halve the bank conflicts of the
+// 32-byte-strided pattern (arrays must be 16-byte aligned and hold NT*M elements) ---------------------------------------------
+template <int M>
+__device__ __forceinline__ void load_chunk(const double* a, int r0, double (&v)[M]) {
+    if constexpr (M % 2 == 0) {
+        const double2* a2 = reinterpret_cast<const double2*>(a + r0);
+#pragma unroll
+        for (int k = 0; k < M / 2; k++) { const double2 t = a2[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < M; k++) v[k] = a[r0 + k];
+    }
+}
+template <int M>
+__device__ __forceinline__ void store_chunk(double* a, int r0, const double (&v)[M]) {
+    if constexpr (M % 2 == 0) {
+        double2* a2 = reinterpret_cast<double2*>(a + r0);
+#pragma unroll
+        for (int k = 0; k < M / 2; k++) a2[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < M; k++) a[r0 + k] = v[k];
+    }
+}
+
+// Inclusive scan of a[0..n) (array of NT*M elements, entries >= n ignored), chunk per thread, in place.
+template <int M>
+__device__ inline void block_inclusive_scan_chunked(double* a, const int n, double* red) {
+    const int tid = threadIdx.x, NT = blockDim.x, r0 = tid * M;
+    double v[M];
+    load_chunk<M>(a, r0, v);
+    double loc = 0;
+#pragma unroll
+    for (int k = 0; k < M; k++) { loc += (r0 + k < n) ? v[k] : 0.0; v[k] = loc; }
+    double s = loc;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    __syncthreads();
+    if (lane == 31) red[w] = s;
+    __syncthreads();
+    double woff = 0;
+    for (int k = 0; k < w; k++) woff += red[k];
+    const double off = woff + (s - loc);
+#pragma unroll
+    for (int k = 0; k < M; k++) v[k] += off;
+    store_chunk<M>(a, r0, v);
+    __syncthreads();
+    (void)NT;
+}
+
 // ---- tridiagonal solve by substructuring ---------------------------------------------------------------------------------------------
 // Rows [r0, r0+M) belong to thread t (r0 = t*M); the last row of each chunk is a separator.  A,B,C,D: sub, diag, super, rhs in
 // shared memory (n rows, n <= NT*M); solution left in D.  `red` needs 4*NT doubles of scratch.
 template <int M>
-__device__ inline void tridiag_substructured(double* A, double* B, double* C, double* D, const int n, double* red) {
+__device__ inline void tridiag_substructured(double* A, double* B, double* C, double* D, const int n, double* red, const bool chunked = false) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int r0 = tid * M;
     double a[M], b[M], c[M], d[M];
+    if (chunked) { load_chunk<M>(A, r0, a); load_chunk<M>(B, r0, b); load_chunk<M>(C, r0, c); load_chunk<M>(D, r0, d); }
 #pragma unroll
     for (int k = 0; k < M; k++) {
         const int i = r0 + k;
-        if (i < n) { a[k] = A[i]; b[k] = B[i]; c[k] = C[i]; d[k] = D[i]; }
+        if (i < n) { if (!chunked) { a[k] = A[i]; b[k] = B[i]; c[k] = C[i]; d[k] = D[i]; } }
         else { a[k] = 0; b[k] = 1; c[k] = 0; d[k] = 0; }
     }
     if (r0 + M - 1 >= n - 1 && r0 < n) {     // the chunk holding the last row: its trailing rows are identity rows
@@ -368,15 +455,13 @@ __device__ inline void tridiag_substructured(double* A, double* B, double* C, do
     __syncthreads();
     const double xLm = (tid > 0) ? Fa[tid - 1] : 0.0;
     // back-substitute the interiors and write the solution
+    double x[M];
 #pragma unroll
-    for (int k = 0; k < M; k++) {
-        const int i = r0 + k;
-        if (i < n) {
-            double x;
-            if (k == M - 1) x = xL;
-            else x = (d[k] - a[k] * xLm - c[k] * xL) * frcp(b[k]);
-            D[i] = x;
-        }
+    for (int k = 0; k < M; k++) x[k] = (k == M - 1) ? xL : (d[k] - a[k] * xLm - c[k] * xL) * frcp(b[k]);
+    if (chunked) store_chunk<M>(D, r0, x);
+    else {
+#pragma unroll
+        for (int k = 0; k < M; k++) if (r0 + k < n) D[r0 + k] = x[k];
     }
     __syncthreads();
 }
@@ -596,20 +681,20 @@ __global__ void __launch_bounds__(256, 2) k_rad2(DevParams p) {
 // Same arithmetic as rad_simple_phase_v2 for S == 1; thread t owns cells t, t+NT, ... in every loop, so rho, T, dS never go
 // through shared memory, and eta1 / 1/denom / T are parked in the shared arrays that are dead while the J system is solved.
 template <int CPT>
-__device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col, double* sm, const double ddt, const double tnow) {
+__device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, double* sm, const double ddt, const double tnow,
+                                             double (&u1)[CPT], double (&u2)[CPT], double (&u3)[CPT], TailAcc& acc, int& negJ_out,
+                                             double& negJval_out) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int N = p.N, N2 = p.N2, Bin = p.Bin;
+    const int NS = NT * CPT;           // padded array length: every thread can touch its 16-byte aligned chunk of CPT entries
     double* TO = sm;                   // total_opacity (out band 0); parks eta1 during the solve
-    double* JJ = TO + N2;              // J; parks T during the solve
-    double* TAU = JJ + N2;             // scan workspace, then the interface diffusion coefficients; parks 1/denom during the solve
-    double* A = TAU + N2; double* B = A + N2; double* C = B + N2; double* D = C + N2;
-    double* red = D + N2;              // 32 + 4*NT
+    double* JJ = TO + NS;              // J; parks T during the solve
+    double* TAU = JJ + NS;             // scan workspace, then the interface diffusion coefficients; parks 1/denom during the solve
+    double* A = TAU + NS; double* B = A + NS; double* C = B + NS; double* D = C + NS;
+    double* red = D + NS;              // 32 + 4*NT
     const int KA = Bin + 2 * p.Bout;
     const SpeciesConst sc = p.sp[0];
     const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1, icv = 1.0 / sc.cv;
-    double* __restrict__ U1 = p.u + idx_u(p, 0, col, 0, 0);
-    double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
-    double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
     double* __restrict__ Jg = p.J + idx_J(p, col, 0, 0);
     double* __restrict__ EI = p.eint + idx_s(p, col, 0, 0);
     double rho[CPT], T[CPT], dS[CPT];
@@ -618,7 +703,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
         const int j = tid + k * NT;
         rho[k] = 1; T[k] = 1; dS[k] = 0;
         if (j < N2) {
-            const double a1 = U1[j], a2 = U2[j], a3 = U3[j];
+            const double a1 = u1[k], a2 = u2[k], a3 = u3[k];
             const double rin = frcp(a1), v = a2 * rin;
             rho[k] = a1;
             T[k] = gm1 * (a3 - 0.5 * a2 * v) * rin * igm1 * icv;
@@ -639,7 +724,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
             if (j >= 1 && j <= N) TAU[N - j] = (kap * rho[k]) * __ldg(p.dx + j);
         }
         __syncthreads();
-        block_inclusive_scan(TAU, N, red);
+        block_inclusive_scan_chunked<CPT>(TAU, N, red);
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int j = tid + k * NT;
@@ -759,7 +844,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
         }
         __syncthreads();
     } else {
-        tridiag_substructured<CPT>(A, B, C, D, N2, red + 32);
+        tridiag_substructured<CPT>(A, B, C, D, N2, red + 32, true);
     }
     // ---- J, T update, e <- T, p <- e, cons <- prim, step tail ------------------------------------------------------------------------------------
     int jneg = 0;
@@ -774,7 +859,6 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
         }
     }
     const int Jswitch = block_or(jneg) || (tnow > 1e15);
-    TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
     int negJ = 0; double negJval = 0;
     const bool allowJ = p.use_planetary_temperature && (D[N] > 0);
 #pragma unroll
@@ -787,7 +871,7 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
                 else if (!(j < N && allowJ)) { negJ = 1; negJval = Jv; }
             }
             Jg[j] = Jv;
-            const double a1 = U1[j], a2 = U2[j], a3 = U3[j];
+            const double a1 = u1[k], a2 = u2[k], a3 = u3[k];
             const double rin = frcp(a1), v = a2 * rin;
             const double pr = gm1 * (a3 - 0.5 * a2 * v);
             const double e_old = pr * rin * igm1;
@@ -802,13 +886,38 @@ __device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col,
             const double e = Tn * sc.cv;
             const double pn = e * a1 * gm1;
             const double m2 = a1 * v;
-            U2[j] = m2; U3[j] = pn * igm1 + 0.5 * m2 * v;
+            u2[k] = m2; u3[k] = pn * igm1 + 0.5 * m2 * v;
             tail_cell2(p, EI, j, v, cs_old, e, Tn, acc);
         }
     }
-    negJ = block_or(negJ);
-    tail_commit(p, col, acc, red, negJ != 0, negJval);
+    negJ_out = block_or(negJ);
+    negJval_out = negJval;
 }
+
+// Stand-alone radiation phase of one single-species column: u from / to HBM around rad1_core_v3.
+template <int CPT>
+__device__ __forceinline__ void rad1_phase_v3(const DevParams& p, const int col, double* sm, const double ddt, const double tnow) {
+    const int tid = threadIdx.x, NT = blockDim.x, N2 = p.N2;
+    double* __restrict__ U1 = p.u + idx_u(p, 0, col, 0, 0);
+    double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
+    double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
+    double u1[CPT], u2[CPT], u3[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        if (j < N2) { u1[k] = U1[j]; u2[k] = U2[j]; u3[k] = U3[j]; } else { u1[k] = 1; u2[k] = 0; u3[k] = 1; }
+    }
+    TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
+    int negJ = 0; double negJval = 0;
+    rad1_core_v3<CPT>(p, col, sm, ddt, tnow, u1, u2, u3, acc, negJ, negJval);
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        if (j < N2) { U2[j] = u2[k]; U3[j] = u3[k]; }
+    }
+    tail_commit(p, col, acc, sm + 7 * NT * CPT, negJ != 0, negJval);
+}
+
 
 template <int CPT>
 __global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
@@ -817,6 +926,75 @@ __global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
     const ColState& c = p.cs[col];
     if (!c.in_step) return;
     rad1_phase_v3<CPT>(p, col, sm, c.dt, c.t);
+}
+
+// ---- fused, persistent step kernel for single-species columns ------------------------------------------------------------------
+// One CTA advances its column by up to `p.steps_per_launch` time steps: step head -> both hydro stages -> [radiation] -> step
+// tail, with the conserved state in registers and the column's clock (ColState) in shared memory for the whole launch.  HBM sees
+// u once per launch instead of four times per step; J, primlast and the static tables are re-read through L2.
+template <int CPT>
+__global__ void __launch_bounds__(256, 3) k_step1(DevParams p) {
+    AIO_DYN_SMEM(double, sm);
+    __shared__ ColState s_cs;
+    __shared__ double s_p2v;
+    const int col = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, N2 = p.N2;
+    if (tid == 0) s_cs = p.cs[col];
+    const SpeciesConst sc = p.sp[0];
+    const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1;
+    double* __restrict__ U1 = p.u + idx_u(p, 0, col, 0, 0);
+    double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
+    double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
+    double u1[CPT], u2[CPT], u3[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int j = tid + k * NT;
+        if (j < N2) { u1[k] = U1[j]; u2[k] = U2[j]; u3[k] = U3[j]; } else { u1[k] = 1; u2[k] = 0; u3[k] = 1; }
+    }
+    double prim2_speed = p.prim2v[col];
+    double* red = sm + ((p.use_rad_fluxes == 2) ? max(9 * N2, 7 * NT * CPT) : 9 * N2);
+    bool touched = false;
+    for (int it = 0; it < p.steps_per_launch; it++) {
+        const StepInfo si = step_head_on(p, s_cs);
+        if (!si.active) break;
+        touched = true;
+        if (si.snap) hydro_snapshot_v2(p, col);
+        hydro_stages_v2<CPT>(p, col, 0, sc, sm, si.dt, si.t_old, u1, u2, u3, prim2_speed);
+        TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
+        int negJ = 0; double negJval = 0;
+        __syncthreads();
+        if (p.use_rad_fluxes == 2) {
+            rad1_core_v3<CPT>(p, col, sm, si.dt, si.t_old + si.dt, u1, u2, u3, acc, negJ, negJval);
+        } else {
+            double* EI = p.eint + idx_s(p, col, 0, 0);
+#pragma unroll
+            for (int k = 0; k < CPT; k++) {
+                const int j = tid + k * NT;
+                if (j < N2) {
+                    const double rin = frcp(u1[k]);
+                    const double v = u2[k] * rin;
+                    const double pr = gm1 * (u3[k] - 0.5 * u2[k] * v);
+                    const double e = pr * rin * igm1;
+                    tail_cell2(p, EI, j, v, fsqrt((gm1 + 1) * gm1 * e), e, e / sc.cv, acc);
+                }
+            }
+        }
+        // prim[2].speed as the next step's 'fixed' boundary sees it (init_and_bounds.cpp:1856)
+#pragma unroll
+        for (int k = 0; k < CPT; k++) if (tid + k * NT == 2) s_p2v = u2[k] / u1[k];
+        __syncthreads();
+        tail_commit_on(s_cs, acc, red, negJ != 0, negJval);
+        __syncthreads();
+        if (N2 > 2) prim2_speed = s_p2v;
+    }
+    if (touched) {
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < N2) { U1[j] = u1[k]; U2[j] = u2[k]; U3[j] = u3[k]; if (j == 2) p.prim2v[col] = prim2_speed; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) p.cs[col] = s_cs;
 }
 
 }  // namespace aio

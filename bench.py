@@ -222,7 +222,7 @@ def main():
     dom = max(("hydro", "radiation"), key=lambda k: kt[k])
     dom_bytes = (BYTES_HYDRO if dom == "hydro" else BYTES_RAD) * ncols * N * S
     achieved = dom_bytes / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_hydro" if dom == "hydro" else "k_rad_simple", "achieved": achieved, "peak": peak_gbs,
+    roofline = {"bound": "hbm", "kernel": "k_hydro2<4>" if dom == "hydro" else "k_rad3<4>", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kt, "step_frac": BYTES_PER_UPDATE * ncols * N * S / (ms / args.steps * 1e-3) / 1e9 / peak_gbs}
 

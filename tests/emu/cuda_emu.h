@@ -26,6 +26,8 @@
 #define __shared__ static
 #define __restrict__
 
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3_emu { unsigned x, y, z; };
 
