@@ -136,9 +136,11 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
     const bool second = (p.order == 2);
     const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1;
     const bool is_gas = !sc.is_dust_like;
-    const double* __restrict__ DPM = p.dpm + idx_s(p, col, s, 0);
-    const double* __restrict__ DPP = p.dpp + idx_s(p, col, s, 0);
-    const double* __restrict__ GS = p.gsrc + idx_s(p, col, s, 0);
+    // plain (coherent) loads: these tables are rewritten by this CTA at steps 0 and 1, possibly within the same launch, so the
+    // non-coherent read-only path (__ldg / const __restrict__) must not be used on them
+    const double* DPM = p.dpm + idx_s(p, col, s, 0);
+    const double* DPP = p.dpp + idx_s(p, col, s, 0);
+    const double* GS = p.gsrc + idx_s(p, col, s, 0);
     double d1[CPT], d2[CPT], d3[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; k++) d1[k] = d2[k] = d3[k] = 0;
@@ -182,7 +184,7 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
                 double lr = rho, lv = v, lp = pr0, rr = rho, rv = v, rp = pr0;
                 double dpm = 0, dpp = 0;
                 if (is_gas) {
-                    dpm = __ldg(DPM + i); dpp = __ldg(DPP + i);
+                    dpm = DPM[i]; dpp = DPP[i];
                     if (i > 0) lp = pr0 + rho * dpm;
                     if (i <= N) rp = pr0 + rho * dpp;
                     if (lp < 0 || rp < 0) { lp = pr0; rp = pr0; }
@@ -191,8 +193,8 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
                     const double rhom = Pr[i - 1], rhop = Pr[i + 1];
                     double dp_l = 0, dp_r = 0;
                     if (is_gas) {
-                        dp_l = rho * dpm - rhom * __ldg(DPP + i - 1);
-                        dp_r = rho * dpp - rhop * __ldg(DPM + i + 1);
+                        dp_l = rho * dpm - rhom * DPP[i - 1];
+                        dp_r = rho * dpp - rhop * DPM[i + 1];
                     }
                     const double cF = __ldg(p.g_cF + i), cB = __ldg(p.g_cB + i), ixF = __ldg(p.g_idxF + i), ixB = __ldg(p.g_idxB + i);
                     const double wl = __ldg(p.g_wl + i), wr = __ldg(p.g_wr + i);
@@ -226,7 +228,7 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
             const int j = tid + k * NT;
             double t1 = 0, t2 = 0, t3 = 0;
             if (j >= 1 && j <= N) {
-                const double g = __ldg(GS + j);
+                const double g = GS[j];
                 const double s2 = (u1[k] * (-1.)) * g, s3 = (u2[k] * (-1.)) * g;
                 const double sp2 = -(__ldg(p.spp_left + j) * Lp[j] - __ldg(p.spp_right + j) * Rp[j]);
                 const double sl = __ldg(p.surf + j - 1), sr = __ldg(p.surf + j), iv = __ldg(p.g_ivol + j);
@@ -286,9 +288,6 @@ __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col
         double* __restrict__ U1 = p.u + idx_u(p, 0, col, s, 0);
         double* __restrict__ U2 = p.u + idx_u(p, 1, col, s, 0);
         double* __restrict__ U3 = p.u + idx_u(p, 2, col, s, 0);
-        const double* __restrict__ DPM = p.dpm + idx_s(p, col, s, 0);
-        const double* __restrict__ DPP = p.dpp + idx_s(p, col, s, 0);
-        const double* __restrict__ GS = p.gsrc + idx_s(p, col, s, 0);
         double u1[CPT], u2[CPT], u3[CPT];
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
