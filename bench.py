@@ -220,9 +220,13 @@ def main():
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
     dom = max(("hydro", "radiation"), key=lambda k: kt[k])
-    dom_bytes = (BYTES_HYDRO if dom == "hydro" else BYTES_RAD) * ncols * N * S
+    fused = kt["radiation"] == 0.0            # single-species decks run the whole step in one persistent kernel (k_step1)
+    dom_bytes = (BYTES_PER_UPDATE if fused else BYTES_HYDRO if dom == "hydro" else BYTES_RAD) * ncols * N * S
+    if fused:
+        kt = {"step": kt["hydro"]}
+        dom = "step"
     achieved = dom_bytes / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_hydro2<4>" if dom == "hydro" else "k_rad3<4>", "achieved": achieved, "peak": peak_gbs,
+    roofline = {"bound": "hbm", "kernel": "k_step1<4>" if fused else "k_hydro2<4>" if dom == "hydro" else "k_rad3<4>", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kt, "step_frac": BYTES_PER_UPDATE * ncols * N * S / (ms / args.steps * 1e-3) / 1e9 / peak_gbs}
 
