@@ -287,13 +287,14 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_fric = 64 * sizeof(double);
     im->smem_rad2 = ((size_t)(5 * S + 7) * N2 + 32 + 4 * NT) * sizeof(double);
     im->smem_rad3 = ((size_t)7 * NT * CPT + 32 + 4 * NT) * sizeof(double);
-    im->smem_step1 = std::max(im->smem_hydro, p.use_rad_fluxes == 2 ? im->smem_rad3 : (size_t)0) + 64 * sizeof(double);
+    im->smem_step1 = ((size_t)9 * NT * CPT + 32 + 12 * p.ng + 64) * sizeof(double);
     im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
         throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
 #define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
     SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
+    { auto kf = k_step1<4, 256>; SETSM(kf, im->smem_step1); }
     SETSM(k_step1<1>, im->smem_step1); SETSM(k_step1<2>, im->smem_step1); SETSM(k_step1<4>, im->smem_step1); SETSM(k_step1<8>, im->smem_step1);
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
@@ -417,7 +418,10 @@ void Engine::launch_fused(long long nsteps) {
         switch (im->CPT) {
         case 1: AIO_LAUNCH(k_step1<1>, ncol, NT, im->smem_step1, im->stream, p); break;
         case 2: AIO_LAUNCH(k_step1<2>, ncol, NT, im->smem_step1, im->stream, p); break;
-        case 4: AIO_LAUNCH(k_step1<4>, ncol, NT, im->smem_step1, im->stream, p); break;
+        case 4:
+            if (NT == 256) { auto kf = k_step1<4, 256>; AIO_LAUNCH(kf, ncol, NT, im->smem_step1, im->stream, p); }
+            else AIO_LAUNCH(k_step1<4>, ncol, NT, im->smem_step1, im->stream, p);
+            break;
         default: AIO_LAUNCH(k_step1<8>, ncol, NT, im->smem_step1, im->stream, p); break;
         }
         im->launches++;

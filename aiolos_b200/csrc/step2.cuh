@@ -122,16 +122,17 @@ __device__ __forceinline__ void hllc_flux2(double dl, double ul, double pl, doub
 }
 
 // Both Heun stages of one species on register-resident cells (u1,u2,u3 of the cells this thread owns); `sm` as in hydro_phase_v2.
-template <int CPT>
+template <int CPT, int NTC = 0>
 __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int col, const int s, const SpeciesConst& sc, double* sm,
                                                 const double dt, const double t_old, double (&u1)[CPT], double (&u2)[CPT],
                                                 double (&u3)[CPT], double& prim2_speed) {
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x; const int NT = NTC > 0 ? NTC : (int)blockDim.x;
     const int N = p.N, N2 = p.N2, ng = p.ng;
-    double* Pr = sm;            double* Pv = Pr + N2;  double* Pp = Pv + N2;
-    double* Lr = Pp + N2;       double* Lv = Lr + N2;  double* Lp = Lv + N2;
-    double* Rr = Lp + N2;       double* Rv = Rr + N2;  double* Rp = Rv + N2;
-    double* win = Rp + N2 + 32;
+    const int LDH = NTC > 0 ? NTC * CPT : N2;      // array stride: a compile-time constant in the specialised instantiation
+    double* Pr = sm;            double* Pv = Pr + LDH;  double* Pp = Pv + LDH;
+    double* Lr = Pp + LDH;      double* Lv = Lr + LDH;  double* Lp = Lv + LDH;
+    double* Rr = Lp + LDH;      double* Rv = Rr + LDH;  double* Rp = Rv + LDH;
+    double* win = Rp + LDH + 32;
     BndWin W; W.w = win; W.ng = ng; W.N2 = N2;
     const bool second = (p.order == 2);
     const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1;
@@ -357,9 +358,9 @@ __device__ __forceinline__ void store_chunk(double* a, int r0, const double (&v)
 }
 
 // Inclusive scan of a[0..n) (array of NT*M elements, entries >= n ignored), chunk per thread, in place.
-template <int M>
+template <int M, int NTC = 0>
 __device__ inline void block_inclusive_scan_chunked(double* a, const int n, double* red) {
-    const int tid = threadIdx.x, NT = blockDim.x, r0 = tid * M;
+    const int tid = threadIdx.x, r0 = tid * M; const int NT = NTC > 0 ? NTC : (int)blockDim.x;
     double v[M];
     load_chunk<M>(a, r0, v);
     double loc = 0;
@@ -384,9 +385,9 @@ __device__ inline void block_inclusive_scan_chunked(double* a, const int n, doub
 // ---- tridiagonal solve by substructuring ---------------------------------------------------------------------------------------------
 // Rows [r0, r0+M) belong to thread t (r0 = t*M); the last row of each chunk is a separator.  A,B,C,D: sub, diag, super, rhs in
 // shared memory (n rows, n <= NT*M); solution left in D.  `red` needs 4*NT doubles of scratch.
-template <int M>
+template <int M, int NTC = 0>
 __device__ inline void tridiag_substructured(double* A, double* B, double* C, double* D, const int n, double* red, const bool chunked = false) {
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x; const int NT = NTC > 0 ? NTC : (int)blockDim.x;
     const int r0 = tid * M;
     double a[M], b[M], c[M], d[M];
     if (chunked) { load_chunk<M>(A, r0, a); load_chunk<M>(B, r0, b); load_chunk<M>(C, r0, c); load_chunk<M>(D, r0, d); }
@@ -679,11 +680,11 @@ __global__ void __launch_bounds__(256, 2) k_rad2(DevParams p) {
 // ---- single-species radiation phase ("v3"): own-cell quantities live in registers, 7 shared arrays (3 CTAs per SM) ----------------
 // Same arithmetic as rad_simple_phase_v2 for S == 1; thread t owns cells t, t+NT, ... in every loop, so rho, T, dS never go
 // through shared memory, and eta1 / 1/denom / T are parked in the shared arrays that are dead while the J system is solved.
-template <int CPT>
+template <int CPT, int NTC = 0>
 __device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, double* sm, const double ddt, const double tnow,
                                              double (&u1)[CPT], double (&u2)[CPT], double (&u3)[CPT], TailAcc& acc, int& negJ_out,
                                              double& negJval_out) {
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x; const int NT = NTC > 0 ? NTC : (int)blockDim.x;
     const int N = p.N, N2 = p.N2, Bin = p.Bin;
     const int NS = NT * CPT;           // padded array length: every thread can touch its 16-byte aligned chunk of CPT entries
     double* TO = sm;                   // total_opacity (out band 0); parks eta1 during the solve
@@ -723,7 +724,7 @@ __device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, 
             if (j >= 1 && j <= N) TAU[N - j] = (kap * rho[k]) * __ldg(p.dx + j);
         }
         __syncthreads();
-        block_inclusive_scan_chunked<CPT>(TAU, N, red);
+        block_inclusive_scan_chunked<CPT, NTC>(TAU, N, red);
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             const int j = tid + k * NT;
@@ -737,7 +738,8 @@ __device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, 
                     const double Sb = F * exp(-rad_jp);
                     dSb = 0.25 * Sb * frcp(dxj) * (1. - p.bond_albedo);
                     const double dtau_tot = -(rad_jp - rad_j);
-                    if (dtau_tot > 1e-3) dSb *= (-expm1(-dtau_tot));
+                    // -expm1(-x) = 1 - exp(-x): above the reference's own series threshold (1e-3) the cancellation costs < 1e-13
+                    if (dtau_tot > 1e-3) dSb *= (1.0 - exp(-dtau_tot));
                     else dSb *= (-fastexpm1_2(-dtau_tot));
                     dSb = smax(dSb, 0.);
                 } else {
@@ -818,8 +820,9 @@ __device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, 
                 eta1 += ddt * dS[k] * frcp(rhos) * icv;
                 e1[k] = eta1; idn[k] = in_;
                 // same (cancelling) form as radiation_simple.cpp:210-211: its round-off is part of what the reference computes
-                const double exd = p.no_rad_trans * rhos * kP * (1 - 4. * C_SIGMA_RAD * Ts3 / C_PI * eta2 * in_);
-                const double exr = p.no_rad_trans * rhos * kP * C_SIGMA_RAD * Ts3 / C_PI * (4 * eta1 * in_ - 3 * Ts);
+                const double sT3 = (C_SIGMA_RAD / C_PI) * Ts3;
+                const double exd = p.no_rad_trans * rhos * kP * (1 - 4. * sT3 * eta2 * in_);
+                const double exr = p.no_rad_trans * rhos * kP * sT3 * (4 * eta1 * in_ - 3 * Ts);
                 d += __ldg(p.vol + j) * exd;
                 r += __ldg(p.vol + j) * exr;
             }
@@ -843,7 +846,7 @@ __device__ __forceinline__ void rad1_core_v3(const DevParams& p, const int col, 
         }
         __syncthreads();
     } else {
-        tridiag_substructured<CPT>(A, B, C, D, N2, red + 32, true);
+        tridiag_substructured<CPT, NTC>(A, B, C, D, N2, red + 32, true);
     }
     // ---- J, T update, e <- T, p <- e, cons <- prim, step tail ------------------------------------------------------------------------------------
     int jneg = 0;
@@ -931,15 +934,15 @@ __global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
 // One CTA advances its column by up to `p.steps_per_launch` time steps: step head -> both hydro stages -> [radiation] -> step
 // tail, with the conserved state in registers and the column's clock (ColState) in shared memory for the whole launch.  HBM sees
 // u once per launch instead of four times per step; J, primlast and the static tables are re-read through L2.
-template <int CPT>
+template <int CPT, int NTC = 0>
 __global__ void __launch_bounds__(256, 3) k_step1(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     __shared__ ColState s_cs;
     __shared__ double s_p2v;
-    const int col = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, N2 = p.N2;
+    const int col = blockIdx.x, tid = threadIdx.x, N2 = p.N2; const int NT = NTC > 0 ? NTC : (int)blockDim.x;
     if (tid == 0) s_cs = p.cs[col];
     const SpeciesConst sc = p.sp[0];
-    const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1;
+    const double gm1 = sc.gm1, igm1 = 1.0 / sc.gm1, icv = 1.0 / sc.cv;
     double* __restrict__ U1 = p.u + idx_u(p, 0, col, 0, 0);
     double* __restrict__ U2 = p.u + idx_u(p, 1, col, 0, 0);
     double* __restrict__ U3 = p.u + idx_u(p, 2, col, 0, 0);
@@ -950,19 +953,20 @@ __global__ void __launch_bounds__(256, 3) k_step1(DevParams p) {
         if (j < N2) { u1[k] = U1[j]; u2[k] = U2[j]; u3[k] = U3[j]; } else { u1[k] = 1; u2[k] = 0; u3[k] = 1; }
     }
     double prim2_speed = p.prim2v[col];
-    double* red = sm + ((p.use_rad_fluxes == 2) ? max(9 * N2, 7 * NT * CPT) : 9 * N2);
+    const int LDH = NTC > 0 ? NTC * CPT : N2;
+    double* red = sm + 9 * LDH;
     bool touched = false;
     for (int it = 0; it < p.steps_per_launch; it++) {
         const StepInfo si = step_head_on(p, s_cs);
         if (!si.active) break;
         touched = true;
         if (si.snap) hydro_snapshot_v2(p, col);
-        hydro_stages_v2<CPT>(p, col, 0, sc, sm, si.dt, si.t_old, u1, u2, u3, prim2_speed);
+        hydro_stages_v2<CPT, NTC>(p, col, 0, sc, sm, si.dt, si.t_old, u1, u2, u3, prim2_speed);
         TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
         int negJ = 0; double negJval = 0;
         __syncthreads();
         if (p.use_rad_fluxes == 2) {
-            rad1_core_v3<CPT>(p, col, sm, si.dt, si.t_old + si.dt, u1, u2, u3, acc, negJ, negJval);
+            rad1_core_v3<CPT, NTC>(p, col, sm, si.dt, si.t_old + si.dt, u1, u2, u3, acc, negJ, negJval);
         } else {
             double* EI = p.eint + idx_s(p, col, 0, 0);
 #pragma unroll
@@ -973,13 +977,13 @@ __global__ void __launch_bounds__(256, 3) k_step1(DevParams p) {
                     const double v = u2[k] * rin;
                     const double pr = gm1 * (u3[k] - 0.5 * u2[k] * v);
                     const double e = pr * rin * igm1;
-                    tail_cell2(p, EI, j, v, fsqrt((gm1 + 1) * gm1 * e), e, e / sc.cv, acc);
+                    tail_cell2(p, EI, j, v, fsqrt((gm1 + 1) * gm1 * e), e, e * icv, acc);
                 }
             }
         }
         // prim[2].speed as the next step's 'fixed' boundary sees it (init_and_bounds.cpp:1856)
 #pragma unroll
-        for (int k = 0; k < CPT; k++) if (tid + k * NT == 2) s_p2v = u2[k] / u1[k];
+        for (int k = 0; k < CPT; k++) if (tid + k * NT == 2) s_p2v = u2[k] * frcp(u1[k]);
         __syncthreads();
         tail_commit_on(s_cs, acc, red, negJ != 0, negJval);
         __syncthreads();
