@@ -54,6 +54,8 @@ _SYMBOLS = {
     "aio_problem_field": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]),
     "aio_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aio_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "aio_upload_state_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "aio_commit_upload": (C.c_int, [C.c_void_p]),
     "aio_column_mass": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aio_write_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "aio_kernel_launches": (C.c_longlong, [C.c_void_p]),
@@ -207,6 +209,14 @@ class Ensemble:
         u = np.ascontiguousarray(u, dtype=np.float64)
         assert u.shape == (3, self.ncols, self.num_species, self.num_cells + 2)
         self._ck(self._lib.aio_upload_state(self._h, u.ctypes.data))
+
+    def upload_state_async(self, u: np.ndarray):
+        """Start copying a (pinned) host state into the staging buffer on the copy stream; pair with commit_upload()."""
+        assert u.dtype == np.float64 and u.flags["C_CONTIGUOUS"] and u.shape == (3, self.ncols, self.num_species, self.num_cells + 2)
+        self._ck(self._lib.aio_upload_state_async(self._h, u.ctypes.data))
+
+    def commit_upload(self):
+        self._ck(self._lib.aio_commit_upload(self._h))
 
     def download_state(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

@@ -194,6 +194,14 @@ int aio_upload_state(aio_ensemble* e, const double* u) {
     if (!e || !u) return fail(AIO_ERR_ARG, "aio_upload_state: bad argument");
     return guarded([&]() { e->eng->upload_u(u); return AIO_OK; });
 }
+int aio_upload_state_async(aio_ensemble* e, const double* u) {
+    if (!e || !u) return fail(AIO_ERR_ARG, "aio_upload_state_async: bad argument");
+    return guarded([&]() { e->eng->upload_u_async(u); return AIO_OK; });
+}
+int aio_commit_upload(aio_ensemble* e) {
+    if (!e) return fail(AIO_ERR_ARG, "null handle");
+    return guarded([&]() { e->eng->commit_upload(); return AIO_OK; });
+}
 int aio_download_state(aio_ensemble* e, double* u) {
     if (!e || !u) return fail(AIO_ERR_ARG, "aio_download_state: bad argument");
     return guarded([&]() { e->eng->download_u(u); return AIO_OK; });

@@ -36,6 +36,8 @@ struct Engine::Impl {
     std::vector<ColState> h_cs;
     double* pinned = nullptr; size_t pinned_bytes = 0;
     double* d_mass = nullptr;
+    // double-buffered host->device staging of the conserved state (end-to-end path): copy stream + events
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_up = nullptr, ev_free = nullptr; double* u_stage = nullptr; bool staged = false;
     bool prof_on = false; cudaEvent_t prof_ev[4] = {nullptr, nullptr, nullptr, nullptr}; double prof_ms[3] = {0, 0, 0};
 
     template <typename T> T* dalloc(size_t n) {
@@ -316,6 +318,7 @@ Engine::~Engine() {
     if (im->ev0) cudaEventDestroy(im->ev0);
     if (im->ev1) cudaEventDestroy(im->ev1);
     for (int k = 0; k < 4; k++) if (im->prof_ev[k]) cudaEventDestroy(im->prof_ev[k]);
+    if (im->copy_stream) { cudaStreamDestroy(im->copy_stream); cudaEventDestroy(im->ev_up); cudaEventDestroy(im->ev_free); }
     if (im->stream) cudaStreamDestroy(im->stream);
     delete im;
 }
@@ -558,6 +561,32 @@ void Engine::upload_u(const double* src) {
     const size_t rows = (size_t)3 * p.ncol * p.S;
     CK(cudaMemcpy2DAsync(p.u, (size_t)p.NP * sizeof(double), src, (size_t)p.N2 * sizeof(double), (size_t)p.N2 * sizeof(double), rows,
                          cudaMemcpyHostToDevice, im->stream));
+}
+// Asynchronous variant for pipelined callers: the copy runs on a second stream into a staging buffer while the compute stream
+// is still stepping; commit_upload() makes the staged state the current one (pointer swap, ordered by events).
+void Engine::upload_u_async(const double* src) {
+    DevParams& p = im->p;
+    const size_t rows = (size_t)3 * p.ncol * p.S;
+    if (!im->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&im->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&im->ev_up)); CK(cudaEventCreate(&im->ev_free));
+        im->u_stage = im->dalloc<double>(rows * p.NP);
+        CK(cudaStreamSynchronize(im->stream));
+        CK(cudaEventRecord(im->ev_free, im->stream));
+    }
+    CK(cudaStreamWaitEvent(im->copy_stream, im->ev_free, 0));      // the staging buffer was the live state until the last swap
+    CK(cudaMemcpy2DAsync(im->u_stage, (size_t)p.NP * sizeof(double), src, (size_t)p.N2 * sizeof(double), (size_t)p.N2 * sizeof(double), rows,
+                         cudaMemcpyHostToDevice, im->copy_stream));
+    CK(cudaEventRecord(im->ev_up, im->copy_stream));
+    im->staged = true;
+}
+void Engine::commit_upload() {
+    if (!im->staged) throw std::invalid_argument("commit_upload without a pending upload_u_async");
+    DevParams& p = im->p;
+    CK(cudaStreamWaitEvent(im->stream, im->ev_up, 0));
+    std::swap(p.u, im->u_stage);
+    CK(cudaEventRecord(im->ev_free, im->stream));                  // kernels launched before this point may still read the old buffer
+    im->staged = false;
 }
 void Engine::download_u(double* dst) {
     DevParams& p = im->p;

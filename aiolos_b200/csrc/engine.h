@@ -26,6 +26,8 @@ public:
     double col_scalar(int col, int which);
     void get_field(int col, int species, int field, double* dst, int n);
     void upload_u(const double* src);
+    void upload_u_async(const double* src);
+    void commit_upload();
     void download_u(double* dst);
     void sync();
     int ncol() const; int num_cells() const; int num_species() const; int num_bands_out() const; int num_bands_in() const;

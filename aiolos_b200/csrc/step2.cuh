@@ -17,7 +17,14 @@
 #include "hydro.cuh"
 #include "rad_simple.cuh"
 
+#ifndef AIO_STEP1_MINB
+#define AIO_STEP1_MINB 3
+#endif
+
 namespace aio {
+
+// loops that only touch shared memory: partial unrolling keeps the hot code in the instruction cache
+constexpr int kUnrollSmem = 8;       // measured: 2 is 4 % slower than full unrolling (profiles/r1f_notes.md)
 
 // ---- branch-free reciprocal / square root ----------------------------------------------------------------------------------
 #ifndef AIO_EMU_BUILD
@@ -177,7 +184,7 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
         __syncthreads();
         prim2_speed = Pv[2 < N2 ? 2 : 0];
         // ---- well-balanced reconstruction (reconstruct.cpp:34-117) ----------------------------------------------------------------
-#pragma unroll
+#pragma unroll kUnrollSmem
         for (int k = 0; k < CPT; k++) {
             const int i = tid + k * NT;
             if (i < N2) {
@@ -212,7 +219,7 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
         }
         __syncthreads();
         // ---- interface fluxes, stored over the (now dead) cell prims ---------------------------------------------------------------
-#pragma unroll
+#pragma unroll kUnrollSmem
         for (int k = 0; k < CPT; k++) {
             const int j = tid + k * NT;
             if (j <= N) {
@@ -935,7 +942,7 @@ __global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
 // tail, with the conserved state in registers and the column's clock (ColState) in shared memory for the whole launch.  HBM sees
 // u once per launch instead of four times per step; J, primlast and the static tables are re-read through L2.
 template <int CPT, int NTC = 0>
-__global__ void __launch_bounds__(256, 3) k_step1(DevParams p) {
+__global__ void __launch_bounds__(256, AIO_STEP1_MINB) k_step1(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     __shared__ ColState s_cs;
     __shared__ double s_p2v;

@@ -239,9 +239,15 @@ def main():
     ens.upload_state(u_host.numpy()); ens.advance(1); ens.column_mass(mass.numpy())
     steps0 = ens.total_steps
     barrier()
+    # pipelined: the H2D copy of step k+1's input (copy stream, second pinned buffer) overlaps step k's kernels
+    u_host2 = u_host.clone().pin_memory()
+    bufs = (u_host.numpy(), u_host2.numpy())
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        ens.upload_state(u_host.numpy())
+    ens.upload_state_async(bufs[0])
+    for k in range(args.e2e_steps):
+        ens.commit_upload()
+        if k + 1 < args.e2e_steps:
+            ens.upload_state_async(bufs[(k + 1) % 2])
         ens.advance(1)
         ens.column_mass(mass.numpy())
         st = ens.status_all()

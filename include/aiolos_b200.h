@@ -93,6 +93,11 @@ int aio_problem_field(aio_ensemble* e, int column, const char* name, double* dst
 /* Conserved state of all columns, host layout [3][ncols][num_species][num_cells+2] (component, column, species, cell). */
 int aio_upload_state(aio_ensemble* e, const double* u_host);
 int aio_download_state(aio_ensemble* e, double* u_host);
+/* Pipelined variant: the copy from (pinned) host memory runs on a second stream into a staging buffer while earlier steps
+ * are still executing; aio_commit_upload makes the staged state current (ordered on the device by events).  u_host must
+ * stay valid and unchanged until the commit. */
+int aio_upload_state_async(aio_ensemble* e, const double* u_host);
+int aio_commit_upload(aio_ensemble* e);
 /* Sum over all columns/species/cells of u1 (mass per column, weighted by cell volume) -- a small result to read back. */
 int aio_column_mass(aio_ensemble* e, double* mass_per_column);
 

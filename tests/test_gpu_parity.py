@@ -124,3 +124,18 @@ def test_from_files_matches_reference(lib, monkeypatch):
     ens.advance(100)
     ref = read_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_k100.bin"))
     assert max(compare_with_golden(ens, ref, column=2).values()) < 1e-8
+
+
+def test_pipelined_upload(lib):
+    """aio_upload_state_async + aio_commit_upload (copy stream, staging buffer) give the same state as the blocking upload."""
+    import torch
+    ens = A.Ensemble.from_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_init.bin"), ncols=64, lib=lib)
+    u0 = torch.from_numpy(ens.download_state()).pin_memory()
+    ens.advance(40)
+    u40 = torch.from_numpy(ens.download_state()).pin_memory()
+    assert not np.array_equal(u0.numpy(), u40.numpy())
+    for buf in (u0, u40, u0):
+        ens.upload_state_async(buf.numpy())
+        ens.advance(1)                      # steps on the *current* state while the copy is in flight
+        ens.commit_upload()
+        assert np.array_equal(ens.download_state(), buf.numpy())
