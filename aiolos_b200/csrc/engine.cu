@@ -30,6 +30,7 @@ struct Engine::Impl {
     bool has_friction = false;
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
     size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
+    bool full_reg = true;           // full FLD: register-resident LU (k_rad_full<NB>); false = shared-memory LU
     bool fused = false;             // single-species persistent step kernel (k_step1)
     int steps_per_launch = 16;
     long long launches = 0;
@@ -489,6 +490,10 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         const int k = atoi(value.c_str());
         if (k < 1 || k > 100000) throw std::invalid_argument("option steps_per_launch: expected 1..100000");
         im->steps_per_launch = k;
+    } else if (key == "full_lu") {
+        if (value == "smem") im->full_reg = false;
+        else if (value == "reg") im->full_reg = true;
+        else throw std::invalid_argument("option full_lu: expected 'reg' or 'smem'");
     } else if (key == "fused") {
         if (value == "0") im->fused = false;
         else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");

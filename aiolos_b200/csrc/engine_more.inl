@@ -36,12 +36,21 @@ void Engine::full_setup() {
 #endif
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (im->smem_full > (size_t)maxsm) throw std::runtime_error("unsupported configuration: full FLD block does not fit in shared memory");
-    CK(cudaFuncSetAttribute(k_rad_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    CK(cudaFuncSetAttribute(k_rad_full<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    CK(cudaFuncSetAttribute(k_rad_full<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    CK(cudaFuncSetAttribute(k_rad_full<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    CK(cudaFuncSetAttribute(k_rad_full<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    CK(cudaFuncSetAttribute(k_rad_full<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
 }
 void Engine::launch_full() {
     DevParams& p = im->p;
     const int wpb = im->nt_full / 32;
-    AIO_LAUNCH(k_rad_full, (p.ncol + wpb - 1) / wpb, im->nt_full, im->smem_full, im->stream, p);
+    const int n = p.Bout + p.S, grid = (p.ncol + wpb - 1) / wpb;
+    if (!im->full_reg) AIO_LAUNCH(k_rad_full<0>, grid, im->nt_full, im->smem_full, im->stream, p);       // option full_lu=smem
+    else if (n <= 8) AIO_LAUNCH(k_rad_full<8>, grid, im->nt_full, im->smem_full, im->stream, p);
+    else if (n <= 16) AIO_LAUNCH(k_rad_full<16>, grid, im->nt_full, im->smem_full, im->stream, p);
+    else if (n <= 24) AIO_LAUNCH(k_rad_full<24>, grid, im->nt_full, im->smem_full, im->stream, p);
+    else AIO_LAUNCH(k_rad_full<32>, grid, im->nt_full, im->smem_full, im->stream, p);
 }
 
 }  // namespace aio

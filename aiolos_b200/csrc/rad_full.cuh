@@ -69,6 +69,7 @@ __device__ __forceinline__ int warp_or(int v) {
     return v;
 }
 
+template <int NB>
 __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -264,45 +265,123 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
         }
         __syncwarp();
 
-        // ---- PartialPivLU of the n x n block, the right-hand-side columns ride along ----------------------------------------
-        for (int k = 0; k < n; k++) {
-            double v = (lane >= k && lane < n) ? fabs(A[lane * LD + k]) : -1.;
-            const double big = warp_max(v);
-            // first row (smallest index) holding the maximum
-            unsigned m = __ballot_sync(0xffffffffu, v == big);
-            const int piv = __ffs(m) - 1;
-            if (big != 0.0) {
-                if (piv != k) {
-                    for (int c = lane; c < NA; c += 32) { const double t = A[k * LD + c]; A[k * LD + c] = A[piv * LD + c]; A[piv * LD + c] = t; }
-                    __syncwarp();
-                }
-                if (lane > k && lane < n) A[lane * LD + k] /= A[k * LD + k];
+        if constexpr (NB > 0) {
+            // ---- register-resident variant: lane r keeps row r of [S | u | rhs] in registers (compile-time indices, fully unrolled);
+            //      the pivot row travels by shuffles, the back substitution runs lane = right-hand-side column out of the tile ----------
+            double a[NB], z[NB];
+#pragma unroll
+            for (int c = 0; c < NB; c++) {
+                a[c] = (lane < n && c < n) ? A[lane * LD + c] : ((c == lane) ? 1. : 0.);
+                z[c] = (lane < n && c <= Bout) ? A[lane * LD + n + c] : 0.;
             }
-            if (lane > k && lane < n) {
-                const double l = A[lane * LD + k];
-                if (l != 0.) {
-                    for (int c = k + 1; c < n; c++) A[lane * LD + c] = d_fnma(l, A[k * LD + c], A[lane * LD + c]);
-                    for (int c = n; c < NA; c++) {
-                        const double z = A[k * LD + c];
-                        if (z != 0.) A[lane * LD + c] = d_fnma(l, z, A[lane * LD + c]);
+            // column c of the u block is zero except in row pos[c] until that row becomes the pivot row (uniform bookkeeping)
+            int pos[NB]; unsigned active = 0;
+#pragma unroll
+            for (int c = 0; c < NB; c++) pos[c] = c;
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                if (k < n) {
+                    const double v = (lane >= k && lane < n) ? fabs(a[k]) : -1.;
+                    const double big = warp_max(v);
+                    const unsigned m = __ballot_sync(0xffffffffu, v == big);
+                    const int piv = __ffs(m) - 1;
+                    if (big != 0.0) {
+                        if (piv != k) {
+                            const int src = (lane == k) ? piv : (lane == piv) ? k : lane;
+#pragma unroll
+                            for (int c = 0; c < NB; c++) { a[c] = __shfl_sync(0xffffffffu, a[c], src); z[c] = __shfl_sync(0xffffffffu, z[c], src); }
+#pragma unroll
+                            for (int c = 0; c < NB; c++) { if (pos[c] == k) pos[c] = piv; else if (pos[c] == piv) pos[c] = k; }
+                        }
+                        const double pv = __shfl_sync(0xffffffffu, a[k], k);
+                        if (lane > k && lane < n) a[k] /= pv;
+                    }
+                    const bool below = (lane > k && lane < n);
+                    const double l = below ? a[k] : 0.;
+#pragma unroll
+                    for (int c = k + 1; c < NB; c++) {
+                        if (c < n) {
+                            const double rk = __shfl_sync(0xffffffffu, a[c], k);
+                            if (below && l != 0.) a[c] = d_fnma(l, rk, a[c]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < NB; c++) {
+                        if (c <= Bout) {
+                            const bool is_rhs = (c == Bout);
+                            if (!is_rhs && !((active >> c) & 1u) && pos[c] == k) active |= (1u << c);
+                            if (is_rhs || ((active >> c) & 1u)) {
+                                const double zk = __shfl_sync(0xffffffffu, z[c], k);
+                                if (zk != 0. && below && l != 0.) z[c] = d_fnma(l, zk, z[c]);
+                            }
+                        }
+                    }
+                }
+            }
+            // rows back into the tile (U in the upper triangle), then lane = right-hand-side column
+#pragma unroll
+            for (int c = 0; c < NB; c++) {
+                if (lane < n && c < n) A[lane * LD + c] = a[c];
+                if (lane < n && c <= Bout) A[lane * LD + n + c] = z[c];
+            }
+            __syncwarp();
+            if (lane < Bout + 1) {
+                double y[NB];
+#pragma unroll
+                for (int k = 0; k < NB; k++) y[k] = (k < n) ? A[k * LD + n + lane] : 0.;
+#pragma unroll
+                for (int k = NB - 1; k >= 0; k--) {
+                    if (k < n && y[k] != 0.) {
+                        y[k] /= A[k * LD + k];
+#pragma unroll
+                        for (int r = 0; r < k; r++) y[r] = d_fnma(y[k], A[r * LD + k], y[r]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; k++) if (k < n) A[k * LD + n + lane] = y[k];
+            }
+            __syncwarp();
+        } else {
+            // ---- PartialPivLU of the n x n block, the right-hand-side columns ride along ----------------------------------------
+            for (int k = 0; k < n; k++) {
+                double v = (lane >= k && lane < n) ? fabs(A[lane * LD + k]) : -1.;
+                const double big = warp_max(v);
+                // first row (smallest index) holding the maximum
+                unsigned m = __ballot_sync(0xffffffffu, v == big);
+                const int piv = __ffs(m) - 1;
+                if (big != 0.0) {
+                    if (piv != k) {
+                        for (int c = lane; c < NA; c += 32) { const double t = A[k * LD + c]; A[k * LD + c] = A[piv * LD + c]; A[piv * LD + c] = t; }
+                        __syncwarp();
+                    }
+                    if (lane > k && lane < n) A[lane * LD + k] /= A[k * LD + k];
+                }
+                if (lane > k && lane < n) {
+                    const double l = A[lane * LD + k];
+                    if (l != 0.) {
+                        for (int c = k + 1; c < n; c++) A[lane * LD + c] = d_fnma(l, A[k * LD + c], A[lane * LD + c]);
+                        for (int c = n; c < NA; c++) {
+                            const double z = A[k * LD + c];
+                            if (z != 0.) A[lane * LD + c] = d_fnma(l, z, A[lane * LD + c]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- back substitution, lane = right-hand-side column (Bout columns of u_i and the rhs) ---------------------------------
+            if (lane < Bout + 1) {
+                const int c = n + lane;
+                for (int k = n - 1; k >= 0; k--) {
+                    double z = A[k * LD + c];
+                    if (z != 0.) {
+                        z /= A[k * LD + k];
+                        A[k * LD + c] = z;
+                        for (int r = 0; r < k; r++) A[r * LD + c] = d_fnma(z, A[r * LD + k], A[r * LD + c]);
                     }
                 }
             }
             __syncwarp();
         }
-        // ---- back substitution, lane = right-hand-side column (Bout columns of u_i and the rhs) ---------------------------------
-        if (lane < Bout + 1) {
-            const int c = n + lane;
-            for (int k = n - 1; k >= 0; k--) {
-                double z = A[k * LD + c];
-                if (z != 0.) {
-                    z /= A[k * LD + k];
-                    A[k * LD + c] = z;
-                    for (int r = 0; r < k; r++) A[r * LD + c] = d_fnma(z, A[r * LD + k], A[r * LD + c]);
-                }
-            }
-        }
-        __syncwarp();
         // ---- keep X_i / A_i for the next cell and for the back sweep -------------------------------------------------------------
         double* Xi = Xg + (size_t)i * n * (Bout + 1);
         for (int k = lane; k < n * (Bout + 1); k += 32) {
