@@ -30,7 +30,8 @@ struct Engine::Impl {
     bool has_friction = false;
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
     size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
-    bool full_reg = true;           // full FLD: register-resident LU (k_rad_full<NB>); false = shared-memory LU
+    bool full_reg = false;          // register-resident LU: measured slower (instruction-cache bound, profiles/r1g); option full_lu=reg
+              // full FLD: register-resident LU (k_rad_full<NB>); false = shared-memory LU
     bool fused = false;             // single-species persistent step kernel (k_step1)
     int steps_per_launch = 16;
     long long launches = 0;

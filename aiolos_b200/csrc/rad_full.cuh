@@ -70,7 +70,7 @@ __device__ __forceinline__ int warp_or(int v) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
+__global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int col = blockIdx.x * wpb + wib;
@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
             }
             __syncwarp();
         } else {
-            // ---- PartialPivLU of the n x n block, the right-hand-side columns ride along ----------------------------------------
+            // ---- PartialPivLU of the n x n block, the right-hand-side columns ride along (tile row = [S | u | rhs], so one
+            //      contiguous sweep over columns k+1..NA-1 updates both; multiplying the structural zeros of the u block is exact) -----
             for (int k = 0; k < n; k++) {
                 double v = (lane >= k && lane < n) ? fabs(A[lane * LD + k]) : -1.;
                 const double big = warp_max(v);
@@ -359,24 +360,25 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
                 if (lane > k && lane < n) {
                     const double l = A[lane * LD + k];
                     if (l != 0.) {
-                        for (int c = k + 1; c < n; c++) A[lane * LD + c] = d_fnma(l, A[k * LD + c], A[lane * LD + c]);
-                        for (int c = n; c < NA; c++) {
-                            const double z = A[k * LD + c];
-                            if (z != 0.) A[lane * LD + c] = d_fnma(l, z, A[lane * LD + c]);
-                        }
+                        const double* __restrict__ rk = A + k * LD;
+                        double* __restrict__ rl = A + lane * LD;
+#pragma unroll 4
+                        for (int c = k + 1; c < NA; c++) rl[c] = d_fnma(l, rk[c], rl[c]);
                     }
                 }
                 __syncwarp();
             }
             // ---- back substitution, lane = right-hand-side column (Bout columns of u_i and the rhs) ---------------------------------
             if (lane < Bout + 1) {
-                const int c = n + lane;
+                double* __restrict__ col_ = A + n + lane;
                 for (int k = n - 1; k >= 0; k--) {
-                    double z = A[k * LD + c];
+                    double z = col_[k * LD];
                     if (z != 0.) {
                         z /= A[k * LD + k];
-                        A[k * LD + c] = z;
-                        for (int r = 0; r < k; r++) A[r * LD + c] = d_fnma(z, A[r * LD + k], A[r * LD + c]);
+                        col_[k * LD] = z;
+                        const double* uk = A + k;
+#pragma unroll 4
+                        for (int r = 0; r < k; r++) col_[r * LD] = d_fnma(z, uk[r * LD], col_[r * LD]);
                     }
                 }
             }
@@ -384,12 +386,12 @@ __global__ void __launch_bounds__(64) k_rad_full(DevParams p) {
         }
         // ---- keep X_i / A_i for the next cell and for the back sweep -------------------------------------------------------------
         double* Xi = Xg + (size_t)i * n * (Bout + 1);
-        for (int k = lane; k < n * (Bout + 1); k += 32) {
-            const int r = k / (Bout + 1), c = k - r * (Bout + 1);
-            const double v = A[r * LD + n + c];
-            Xp[r * LDX + c] = v;
-            Xi[k] = v;
-        }
+        if (lane <= Bout)
+            for (int r = 0; r < n; r++) {
+                const double v = A[r * LD + n + lane];
+                Xp[r * LDX + lane] = v;
+                Xi[r * (Bout + 1) + lane] = v;
+            }
         __syncwarp();
     }
 
