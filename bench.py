@@ -227,7 +227,11 @@ def main():
         dom = "step"
     achieved = dom_bytes / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_step1<4>" if fused else "k_hydro2<4>" if dom == "hydro" else "k_rad3<4>", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak_gbs,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k_step1<4,256> launch (16 steps, 4096 columns) from the
+                # ncu --set full capture profiles/r1e_ncu_full_k_step1.txt, per time step: (267.6 + 191.9) MB / 16
+                "traffic": (28.7e6 if (fused and ncols == 4096) else None), "traffic_unit": "bytes per step (all columns)",
+                "algorithmic_bytes": BYTES_PER_UPDATE * ncols * N * S if fused else dom_bytes, "peak_source": peak_src,
                 "kernel_ms": kt, "step_frac": BYTES_PER_UPDATE * ncols * N * S / (ms / args.steps * 1e-3) / 1e9 / peak_gbs}
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------------
