@@ -22,7 +22,13 @@ lib_path = os.path.join(_HERE, "libaiolos_b200.so")
 
 FIELDS = {"u1": 0, "u2": 1, "u3": 2, "eint_last": 3, "phi": 4, "phi_s": 5, "dS": 6, "temperature": 7, "pres": 8,
           "speed": 9, "J": 16}
-COL_STATES = {0: "ok", 1: "negative_T", 2: "negative_J", 3: "nan"}
+COL_STATES = {0: "ok", 1: "negative_T", 2: "negative_J", 3: "nan", 4: "hook_out_of_window"}
+
+
+def plugin_lib_path(name: str) -> str:
+    """In-tree library built with a problem plugin: ``make -C aiolos_b200/csrc PROBLEM=<.../name.cpp>`` (the reference's
+    ``make PROBLEM=name``, makefile:22,28-29).  Pass it as ``lib=`` to ``Ensemble.from_files``."""
+    return os.path.join(_HERE, f"libaiolos_b200_{name}.so")
 
 
 class AiolosError(RuntimeError):

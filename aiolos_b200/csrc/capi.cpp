@@ -1,6 +1,7 @@
 // C ABI of aiolos_b200 (include/aiolos_b200.h): thin exception-to-error-code layer over aio::Engine.
 #include "aiolos_b200.h"
 #include "engine.h"
+#include "hooks.h"
 #include "cuda_compat.h"
 #include <cmath>
 #include <cstring>
@@ -64,10 +65,13 @@ extern "C" {
 const char* aio_last_error(void) { return g_err.c_str(); }
 const char* aio_version(void) {
 #ifdef AIO_EMU_BUILD
-    return "aiolos_b200 0.1 (CTA emulator, test build)";
+    static const std::string base = "aiolos_b200 0.1 (CTA emulator, test build)";
 #else
-    return "aiolos_b200 0.1 (sm_100a)";
+    static const std::string base = "aiolos_b200 0.1 (sm_100a)";
 #endif
+    // a library made with `make PROBLEM=<file>` names the problem plugin it carries (hooks.h)
+    static const std::string full = aio::hooks_compiled() ? base + " problem=" + aio::hooks_name() : base;
+    return full.c_str();
 }
 
 int aio_device_count(void) {

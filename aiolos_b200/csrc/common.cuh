@@ -20,7 +20,8 @@ namespace aio {
 constexpr int MAXS = 16;        // species per column supported by the generic kernels
 constexpr int MAXB = 32;        // radiation bands (in or out)
 
-enum ColStatus : int { COL_OK = 0, COL_NEG_T = 1, COL_NEG_J = 2, COL_NAN = 3 };
+enum ColStatus : int { COL_OK = 0, COL_NEG_T = 1, COL_NEG_J = 2, COL_NAN = 3,
+                       COL_HOOK_RANGE = 4 };   // a plugin boundary hook touched a cell outside its boundary window
 
 struct ColState {               // per-column clock and step-control scalars (c_Sim members, aiolos.h:458-476)
     double t;                   // globalTime
@@ -53,6 +54,7 @@ struct SpeciesConst {           // per-species constants (c_Species + IdealGas_E
     double wave_amplitude, wave_period;
     double shock_ul[3], shock_ur[3], background_u[3];
     double prim2_speed;         // prim[2].speed as seen by the 'fixed' BC
+    double initial_fraction, density_excess, degrees_of_freedom;   // read by plugin hooks only
     int is_dust_like;
     int bc_left, bc_right;      // BoundaryType
     int use_wave;
@@ -97,6 +99,7 @@ struct DevParams {
     const SpeciesConst* sp;             // [S]
     // per-column state
     double *u, *eint, *phi, *phis, *J, *dS;
+    const double *phiN;                 // [ncol] phi[num_cells] as update_mass_and_pot() recomputes it every step (see phi_snapshot)
     double *dSband_top;                 // [ncol][Bin] dS_band(N,b) of the previous step (radiation.cpp:263-265)
     // v2 kernels (step2.cuh): tabulated slope-limiter factors / inverse volumes [NP], shared by all columns, and the static
     // per-column hydrostatic offsets and gravity source coefficient [ncol][S][NP]
@@ -108,6 +111,7 @@ struct DevParams {
     const double *opa_data;             // tabulated opacities of all species, see OpaTable
     const struct OpaTable *opa_tab;     // [S]
     double T_star;
+    double R_star, planet_semimajor, star_mass, UV_star, X_star, domain_min, domain_max;   // read by plugin hooks only
     double *Xstore;                     // full FLD: [ncol][N2][n][Bout+1]  X_i = S_i^-1 u_i and S_i^-1 rhs_i (rad_full.cuh)
     double *Tsave, *cssave;             // [ncol][S][NP] prim.temperature / prim.sound_speed as left by the post-hydro
                                         // compute_pressure: friction changes u but not these (source.cpp:485-505), and the
@@ -128,6 +132,14 @@ __host__ __device__ inline size_t idx_s(const DevParams& p, int col, int s, int 
 __host__ __device__ inline size_t idx_c(const DevParams& p, int col, int j) { return (size_t)col * p.NP + j; }
 __host__ __device__ inline size_t idx_J(const DevParams& p, int col, int b, int j) {
     return ((size_t)col * p.Bout + b) * p.NP + j;
+}
+
+// phi as update_kzz_and_gravpot() sees it at the start of a step.  update_mass_and_pot() rewrites phi[2..num_cells] every step
+// (source.cpp:60-77); index num_cells is a ghost cell at order 2, so whatever a right-hand boundary condition wrote there during
+// the previous step (reflecting / periodic / user hook: phi[ghost] = phi[active]) is undone before phi_s is refreshed, while
+// the outermost entry num_cells+1 and the entries 0, 1 keep the boundary condition's value.
+__device__ __forceinline__ double phi_snapshot(const DevParams& p, int col, const double* phi, int j) {
+    return (j == p.N) ? p.phiN[col] : phi[j];
 }
 
 // physical constants, verbatim values of aiolos.h:47-77

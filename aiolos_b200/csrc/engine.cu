@@ -3,6 +3,7 @@
 // One time step of every still-active column = one launch sequence  k_hydro -> [k_friction] -> [k_rad_*],
 // i.e. c_Sim::execute()'s loop body (reference advection.cpp:60-348) with one CTA per column.
 #include "engine.h"
+#include "hooks.h"
 #include "common.cuh"
 #include "hydro.cuh"
 #include "friction.cuh"
@@ -100,7 +101,8 @@ static void check_supported(const Problem& q) {
     if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
     if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
     for (auto& sp : q.species) {
-        if (sp.boundary_left == 0 || sp.boundary_right == 0) fail("user boundary hooks (compile a problem plugin, INTEGRATION.md)");
+        if ((sp.boundary_left == 0 || sp.boundary_right == 0) && !hooks_compiled())
+            fail("user boundary hooks (PARI_BOUND_TYPE 0) need a library built with a problem plugin: make PROBLEM=<file>, INTEGRATION.md");
     }
 }
 
@@ -188,6 +190,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
         for (int k = 0; k < 3; k++) { c.shock_ul[k] = d.SHOCK_TUBE_UL[k]; c.shock_ur[k] = d.SHOCK_TUBE_UR[k]; c.background_u[k] = d.BACKGROUND_U[k]; }
         c.is_dust_like = d.is_dust_like; c.bc_left = d.boundary_left; c.bc_right = d.boundary_right;
         c.prim2_speed = d.prim2_speed_init.empty() ? 0 : d.prim2_speed_init[0];
+        c.initial_fraction = d.initial_fraction; c.density_excess = d.density_excess; c.degrees_of_freedom = d.degrees_of_freedom;
         for (int b = 0; b < p.Bin; b++) {
             double a = b < (int)d.opacity_avg_solar.size() ? d.opacity_avg_solar[b] : 0;
             kap[(size_t)s * KA + b] = (q0.opacity_model == 'P' && d.is_dust_like) ? a : q0.const_opacity_solar_factor * a;
@@ -211,6 +214,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.kappa_avg = im->upload(kap);
     // state-dependent opacity models: tables (T, K) and the per-cell opacity array filled by k_opacity every step
     p.kap_cell = nullptr; p.opa_data = nullptr; p.opa_tab = nullptr; p.T_star = q0.T_star;
+    p.R_star = q0.R_star; p.planet_semimajor = q0.planet_semimajor; p.star_mass = q0.star_mass; p.UV_star = q0.UV_star;
+    p.X_star = q0.X_star; p.domain_min = q0.domain_min; p.domain_max = q0.domain_max;
     if (q0.use_rad_fluxes && (q0.opacity_model == 'T' || q0.opacity_model == 'K' || q0.opacity_model == 'D')) {
         std::vector<double> flat;
         std::vector<OpaTable> tabs(S);
@@ -236,13 +241,14 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     // per-column state
     std::vector<double> hu((size_t)3 * ncol * S * NP, 0.0), he((size_t)ncol * S * NP, 0.0), hphi((size_t)ncol * NP, 0.0);
     std::vector<double> hphis((size_t)ncol * S * NP, 0.0), hJ((size_t)ncol * p.Bout * NP, 0.0), hsol((size_t)ncol * p.Bin, 0.0);
-    std::vector<double> hp2((size_t)ncol * S, 0.0);
+    std::vector<double> hp2((size_t)ncol * S, 0.0), hphiN(ncol, 0.0);
     im->h_cs.assign(ncol, ColState{});
     for (int c = 0; c < ncol; c++) {
         const Problem& q = cols[c];
         std::vector<double> phi = q.phi;
         phi_after_first_update(q, phi);
         for (int j = 0; j < N2; j++) hphi[idx_c(p, c, j)] = phi[j];
+        hphiN[c] = phi[N];
         for (int s = 0; s < S; s++) {
             const SpeciesData& d = q.species[s];
             for (int j = 0; j < N2; j++) {
@@ -260,7 +266,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
         st.T_planet = q.T_planet; st.steps = 0; st.status = COL_OK;
     }
     p.u = im->upload(hu); p.eint = im->upload(he); p.phi = im->upload(hphi); p.phis = im->upload(hphis);
-    p.J = im->upload(hJ); p.solar_heating_final = im->upload(hsol); p.prim2v = im->upload(hp2);
+    p.J = im->upload(hJ); p.solar_heating_final = im->upload(hsol); p.prim2v = im->upload(hp2); p.phiN = im->upload(hphiN);
     p.dS = im->dalloc<double>((size_t)ncol * S * NP);
     p.dpm = im->dalloc<double>((size_t)ncol * S * NP); p.dpp = im->dalloc<double>((size_t)ncol * S * NP);
     p.gsrc = im->dalloc<double>((size_t)ncol * S * NP);
@@ -293,6 +299,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_rad3 = ((size_t)7 * NT * CPT + 32 + 4 * NT) * sizeof(double);
     im->smem_step1 = ((size_t)9 * NT * CPT + 32 + 12 * p.ng + 64) * sizeof(double);
     im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
+    for (auto& sp : q0.species) if (sp.boundary_left == 0 || sp.boundary_right == 0) im->fused = false;   // hooks flag errors through p.cs
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
         throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
@@ -629,3 +636,4 @@ void Engine::sync() { CK(cudaStreamSynchronize(im->stream)); }
 }  // namespace aio
 
 #include "engine_more.inl"
+#include "hooks_glue.inl"

@@ -5,6 +5,7 @@
 // .par file, the value is the second blank-separated token parsed with operator>>, a key present on two lines is an
 // error; species rows start with '@'; opacity files are opened as inputdata/<name> relative to the CWD.
 #include "problem.h"
+#include "hooks.h"
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -93,6 +94,7 @@ struct Spec {
     std::vector<AOSp> prim, primlast;
     std::vector<double> phi_s, K_zzf;
     double SHOCK_TUBE_MID = 0.5;
+    int index = 0;
     std::string opacity_data_string, opacity_corrk_string;
     void cons_from_prim(const AOSp& p, double& u1, double& u2, double& u3) const {
         u1 = p.density; u2 = p.density * p.speed; u3 = p.pres / gm1 + 0.5 * u2 * p.speed;
@@ -331,6 +333,23 @@ void read_species_data(Sim& S, Spec& s, const std::string& filename, int species
     opa_cache[key] = OpaVal{d.opacity_avg_solar, d.opacity_avg_planck, d.opacity_avg_rosseland};
 }
 
+// ---- link-time problem plugin (hooks.h): plain-data view of one species for the glue in engine.cu -------------------------
+HookHost make_hook_host(Sim& S, Spec& s, int si) {
+    Problem& q = S.q; SpeciesData& d = s.d;
+    HookHost h{};
+    h.species_index = si; h.num_cells = q.num_cells; h.num_ghosts = q.num_ghosts; h.num_species = q.num_species;
+    h.num_bands_in = q.num_bands_in; h.num_bands_out = q.num_bands_out; h.is_dust_like = d.is_dust_like;
+    h.mass_amu = d.mass_amu; h.inv_mass = d.inv_mass; h.initial_fraction = d.initial_fraction; h.density_excess = d.density_excess;
+    h.static_charge = d.static_charge; h.cv = d.cv; h.gamma_adiabat = d.gamma_adiabat; h.degrees_of_freedom = d.degrees_of_freedom;
+    h.const_T_space = d.const_T_space; h.const_opacity = d.const_opacity; h.gm1 = s.gm1; h.speciesname = d.speciesname.c_str();
+    h.planet_mass = q.planet_mass; h.planet_semimajor = q.planet_semimajor; h.star_mass = q.star_mass; h.T_star = q.T_star;
+    h.R_star = q.R_star; h.UV_star = q.UV_star; h.X_star = q.X_star; h.domain_min = q.domain_min; h.domain_max = q.domain_max;
+    h.phi = q.phi.data(); h.x_i = q.x_i.data(); h.x_i12 = q.x_i12.data(); h.x_iVC = q.x_iVC.data(); h.dx = q.dx.data();
+    h.surf = q.surf.data(); h.vol = q.vol.data();
+    h.u1 = d.u1.data(); h.u2 = d.u2.data(); h.u3 = d.u3.data();
+    return h;
+}
+
 // ---- boundary conditions on the host (applied once by the constructor, init_and_bounds.cpp:1275-1276,1779-1974) ------------
 void apply_boundaries_host(Sim& S, Spec& s) {
     Problem& q = S.q;
@@ -339,7 +358,7 @@ void apply_boundaries_host(Sim& S, Spec& s) {
     auto prim_of = [&](int i, AOSp& p) { p.density = d.u1[i]; p.speed = d.u2[i] / d.u1[i]; p.pres = s.gm1 * (d.u3[i] - 0.5 * d.u2[i] * p.speed); };
     auto set = [&](int i, const AOSp& p) { s.cons_from_prim(p, d.u1[i], d.u2[i], d.u3[i]); };
     switch (d.boundary_left) {
-    case 0: throw std::runtime_error("unsupported configuration: user boundary hooks (PARI_BOUND_TYPE_LEFT 0)");
+    case 0: { HookHost h = make_hook_host(S, s, s.index); hook_boundary_host(h, 0); break; }    // throws in the stock library
     case 1:
         for (int i = ng; i > 0; i--) {
             AOSp p; prim_of(i, p);
@@ -381,7 +400,7 @@ void apply_boundaries_host(Sim& S, Spec& s) {
     default: break;
     }
     switch (d.boundary_right) {
-    case 0: throw std::runtime_error("unsupported configuration: user boundary hooks (PARI_BOUND_TYPE_RIGHT 0)");
+    case 0: { HookHost h = make_hook_host(S, s, s.index); hook_boundary_host(h, 1); break; }
     case 1:
         for (int i = Ncell + ng; i < Ncell + 2 * ng; i++) {
             AOSp p; prim_of(i - 1, p);
@@ -503,6 +522,7 @@ void initialize_hydrostatic_atmosphere(Sim& S, Spec& s, int species_index, const
 void construct_species(Sim& S, int si, const ParFile& par, const std::string& species_filename) {
     Problem& q = S.q;
     Spec& s = S.sp[si];
+    s.index = si;
     SpeciesData& d = s.d;
     const int N2 = q.num_cells + 2;
     d.boundary_left = par.get<int>("PARI_BOUND_TYPE_LEFT", 3);
@@ -560,7 +580,8 @@ void construct_species(Sim& S, int si, const ParFile& par, const std::string& sp
             s.cons_from_prim(p, d.u1[i], d.u2[i], d.u3[i]);
         }
     } else if (q.problem_number == 0) {
-        throw std::runtime_error("unsupported configuration: PARI_PROBLEM_NUMBER 0 (user_initial_conditions hook)");
+        HookHost h = make_hook_host(S, s, si);                                  // init_and_bounds.cpp:1256-1257
+        hook_initial_conditions(h);                                             // throws in the stock library
     } else {
         for (int i = 0; i < N2; i++) { d.u1[i] = 1; d.u2[i] = 1; d.u3[i] = 1; }
     }

@@ -107,6 +107,11 @@ struct BndWin {
     __device__ double& at(int c, int cell) { int k = (cell < 2 * ng) ? cell : cell - (N2 - 4 * ng); return w[c * 4 * ng + k]; }
 };
 
+#ifdef AIO_PROBLEM_FILE
+// defined in hooks_glue.inl (end of engine.cu), next to the problem file it wraps
+__device__ void hook_boundary(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, int side);
+#endif
+
 __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, double prim2_speed) {
     const int ng = p.ng;
     double* phi = p.phi + idx_c(p, col, 0);
@@ -150,7 +155,11 @@ __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesCons
             phi[i] = phi[iact];
         }
         break; }
-    default: break;  // user hooks: rejected at create time
+    default:         // 0 = user hook (problem plugin); the stock library rejects such decks at create time
+#ifdef AIO_PROBLEM_FILE
+        if (sc.bc_left == 0) hook_boundary(p, sc, col, s, W, 0);
+#endif
+        break;
     }
 }
 
@@ -201,7 +210,11 @@ __device__ inline void apply_boundary_right(const DevParams& p, const SpeciesCon
             prim_to_cons(q, sc.gm1, W.at(0, i), W.at(1, i), W.at(2, i));
         }
         break;
-    default: break;
+    default:
+#ifdef AIO_PROBLEM_FILE
+        if (sc.bc_right == 0) hook_boundary(p, sc, col, s, W, 1);
+#endif
+        break;
     }
 }
 
@@ -273,7 +286,7 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
         const double* phi = p.phi + idx_c(p, col, 0);
         for (int s = 0; s < p.S; s++) {
             double* phis = p.phis + idx_s(p, col, s, 0);
-            for (int j = tid; j < N2; j += NT) phis[j] = phi[j] * 1.0;
+            for (int j = tid; j < N2; j += NT) phis[j] = phi_snapshot(p, col, phi, j) * 1.0;
         }
         __syncthreads();
     }

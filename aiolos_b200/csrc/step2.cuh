@@ -260,7 +260,7 @@ __device__ inline void hydro_snapshot_v2(const DevParams& p, const int col) {
     const double* phi = p.phi + idx_c(p, col, 0);
     for (int s = 0; s < p.S; s++) {
         double* phis = p.phis + idx_s(p, col, s, 0);
-        for (int j = tid; j < N2; j += NT) phis[j] = phi[j] * 1.0;
+        for (int j = tid; j < N2; j += NT) phis[j] = phi_snapshot(p, col, phi, j) * 1.0;
     }
     __syncthreads();
     build_static_tables(p, col);
@@ -282,7 +282,7 @@ __device__ __forceinline__ void hydro_phase_v2(const DevParams& p, const int col
         const double* phi = p.phi + idx_c(p, col, 0);
         for (int s = 0; s < p.S; s++) {
             double* phis = p.phis + idx_s(p, col, s, 0);
-            for (int j = tid; j < N2; j += NT) phis[j] = phi[j] * 1.0;
+            for (int j = tid; j < N2; j += NT) phis[j] = phi_snapshot(p, col, phi, j) * 1.0;
         }
         __syncthreads();
         build_static_tables(p, col);

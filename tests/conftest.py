@@ -27,6 +27,18 @@ def emu_lib():
 
 
 @pytest.fixture(scope="session")
+def emu_plugin_lib():
+    """Emulator build with the reference's own problems/dusty_wind.cpp compiled in (make PROBLEM=..., dev container only)."""
+    src = os.path.join(REF_ROOT, "problems", "dusty_wind.cpp")
+    if not os.path.exists(src):
+        pytest.skip("reference problem files not present (GPU box)")
+    r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu"), "PROBLEM=" + src], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.fail("tests/emu plugin build failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+    return os.path.join(ROOT, "tests", "emu", "_build", "dusty_wind", "libaiolos_emu_dusty_wind.so")
+
+
+@pytest.fixture(scope="session")
 def product_lib():
     import aiolos_b200
     if not os.path.exists(aiolos_b200.lib_path):

@@ -22,6 +22,8 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
+#define __managed__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __restrict__

@@ -42,6 +42,10 @@ CASES = {
     "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", None, [1, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
+    # PBC_model/dusty_wind.par at 1000 instead of 4000 cells per decade (our variant), with the reference linked against its own
+    # problems/dusty_wind.cpp (oracle/_ref/aiolos_ref_dump_dusty_wind): user initial conditions + user boundary hooks on both
+    # sides, gas + dust, numeric friction, opacity model D, full FLD with 3x3 blocks
+    "p1_dusty_wind": ("PBC_model/", "dusty_wind_1k.par", "silicate.spc", [1, 20, 100, 1000], "dusty_wind"),
 }
 
 KEEP_FINAL = ("dt_sequence", "t_max", "t_max_deck", "steps", "globalTime", "dt", "cflfactor", "timestep_rad2", "cfl_step",
@@ -50,14 +54,16 @@ KEEP_SPECIES = ("u1", "u2", "u3", "temperature", "speed", "pres", "eint_last", "
 
 
 def run_case(name):
-    d, par, spc, steps = CASES[name]
+    d, par, spc, steps = CASES[name][:4]
+    dump = DUMP + ("_" + CASES[name][4] if len(CASES[name]) > 4 else "")      # plugin variant of the oracle
     subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), RUN], check=True, stdout=subprocess.DEVNULL)
     for f in os.listdir(os.path.join(HERE, "decks")):        # our own deck variants live next to the reference's test decks
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "test_files", f)], check=True)
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "runs_mdot_vs_euv_plot", f)], check=True)
+        subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "PBC_model", f)], check=True)
     for k in steps:
         out = os.path.join(RUN, f"{name}_k{k}")
-        cmd = [DUMP, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]
+        cmd = [dump, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]
         if spc:
             cmd += ["-spc", spc]
         with open(out + ".log", "w") as log:

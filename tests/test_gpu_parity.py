@@ -139,3 +139,51 @@ def test_pipelined_upload(lib):
         ens.advance(1)                      # steps on the *current* state while the copy is in flight
         ens.commit_upload()
         assert np.array_equal(ens.download_state(), buf.numpy())
+
+
+# ---- link-time problem plugin: the reference's own problems/dusty_wind.cpp compiled into a second library ----------
+@pytest.fixture(scope="module")
+def plugin_lib():
+    path = A.plugin_lib_path("dusty_wind")
+    if not os.path.exists(path):
+        pytest.fail(path + " missing: __graft_entry__.build() makes it in the dev container (needs the reference's problem file)")
+    L = A.load_library(path)
+    assert L.aio_device_count() > 0 and b"sm_100a" in L.aio_version() and b"dusty_wind" in L.aio_version()
+    return path
+
+
+def _dusty_wind(plugin_lib, monkeypatch, ncols=1, overrides=None):
+    from conftest import ROOT
+    monkeypatch.chdir(os.path.join(ROOT, "oracle", "decks"))                  # inputdata/smalldust.opa, relative to the CWD
+    return A.Ensemble.from_files(os.path.join(GOLDEN, "decks") + "/", "dusty_wind_1k.par", "silicate.spc", ncols=ncols,
+                                 overrides=overrides, lib=plugin_lib)
+
+
+@pytest.mark.parametrize("k,tol", [(1, 1e-10), (100, 1e-8), (1000, 1e-8)])
+def test_plugin_dusty_wind_matches_reference(plugin_lib, monkeypatch, k, tol):
+    """User initial conditions (host) + user boundary hooks on both sides (inside the hydro kernel, every Heun stage), gas +
+    dust with numeric friction, opacity model D, full FLD -- against the reference linked with the same problem file."""
+    from aiodump import read_dump
+    ens = _dusty_wind(plugin_lib, monkeypatch)
+    ref = read_dump(os.path.join(GOLDEN, f"p1_dusty_wind_k{k}.bin"))
+    ens.advance(k)
+    st = ens.status(0)
+    assert st["steps"] == k and st["state"] == 0
+    assert abs(st["t"] - ref["globalTime"][0]) <= 1e-9 * ref["globalTime"][0]
+    errs = compare_with_golden(ens, ref)
+    bad = {f: e for f, e in errs.items() if not e <= tol}
+    assert not bad, f"dusty_wind k={k}: {bad}"
+
+
+def test_plugin_dt_sequence_and_ensemble(plugin_lib, monkeypatch):
+    from aiodump import read_dump
+    dts = read_dump(os.path.join(GOLDEN, "p1_dusty_wind_k1000.bin"))["dt_sequence"]
+    ens = _dusty_wind(plugin_lib, monkeypatch, ncols=3, overrides=[(1, "PARI_PLANET_MASS", "0.035")])
+    worst = 0.0
+    for i in range(700):                                                      # the CFL / energy limiters take over at step ~500
+        ens.advance(1)
+        worst = max(worst, abs(ens.status(0)["dt"] - dts[i]) / dts[i], abs(ens.status(2)["dt"] - dts[i]) / dts[i])
+    assert worst < 1e-9, worst
+    a, b, c = (ens.get("u1", col, 1) for col in range(3))
+    assert np.array_equal(a, c) and not np.array_equal(a, b)                  # columns are independent; the override took effect
+    assert (ens.status_all()["state"] == 0).all()
