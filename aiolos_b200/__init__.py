@@ -64,6 +64,7 @@ _SYMBOLS = {
     "aio_commit_upload": (C.c_int, [C.c_void_p]),
     "aio_column_mass": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aio_write_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "aio_write_monitor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "aio_kernel_launches": (C.c_longlong, [C.c_void_p]),
     "aio_total_steps": (C.c_longlong, [C.c_void_p]),
     "aio_last_error": (C.c_char_p, []),
@@ -238,6 +239,10 @@ class Ensemble:
 
     def write_outputs(self, column: int, index: int, outdir: str = ""):
         self._ck(self._lib.aio_write_outputs(self._h, column, index, outdir.encode()))
+
+    def write_monitor(self, column: int, outdir: str = "", truncate: bool = False):
+        """``c_Sim::print_monitor``: one row of monitor_<stem>.dat for this column's current state."""
+        self._ck(self._lib.aio_write_monitor(self._h, column, outdir.encode(), int(truncate)))
 
     @property
     def kernel_launches(self) -> int:

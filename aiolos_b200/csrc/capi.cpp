@@ -11,6 +11,7 @@
 struct aio_ensemble {
     std::unique_ptr<aio::Engine> eng;
     std::vector<aio::Problem> problems;      // host-side description of every column (kept for the writers)
+    std::vector<std::vector<double>> monitor_prev;   // previous_monitor_J / _T per column (io.cpp:1048-1054)
 };
 
 namespace {
@@ -218,6 +219,16 @@ int aio_column_mass(aio_ensemble* e, double* m) {
 int aio_write_outputs(aio_ensemble* e, int column, int index, const char* outdir) {
     if (!e || column < 0 || column >= e->eng->ncol()) return fail(AIO_ERR_ARG, "aio_write_outputs: bad argument");
     return guarded([&]() { aio::write_outputs(*e->eng, e->problems[column], column, index, outdir ? outdir : ""); return AIO_OK; });
+}
+
+int aio_write_monitor(aio_ensemble* e, int column, const char* outdir, int truncate) {
+    if (!e || column < 0 || column >= e->eng->ncol()) return fail(AIO_ERR_ARG, "aio_write_monitor: bad argument");
+    return guarded([&]() {
+        if (e->monitor_prev.size() != (size_t)e->eng->ncol()) e->monitor_prev.assign(e->eng->ncol(), {});
+        if (truncate) e->monitor_prev[column].clear();
+        aio::write_monitor(*e->eng, e->problems[column], column, outdir ? outdir : "", truncate != 0, e->monitor_prev[column]);
+        return AIO_OK;
+    });
 }
 
 long long aio_kernel_launches(aio_ensemble* e) { return e ? e->eng->kernel_launches() : 0; }

@@ -34,6 +34,7 @@ struct Engine::Impl {
     bool full_reg = false;          // register-resident LU: measured slower (instruction-cache bound, profiles/r1g); option full_lu=reg
               // full FLD: register-resident LU (k_rad_full<NB>); false = shared-memory LU
     bool fused = false;             // single-species persistent step kernel (k_step1)
+    int step1_ctas = 3;             // resident CTAs per SM the fused kernel is compiled for (3: 80 registers, 2: 128)
     int steps_per_launch = 16;
     long long launches = 0;
     std::vector<ColState> h_cs;
@@ -306,6 +307,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
 #define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
     SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
     { auto kf = k_step1<4, 256>; SETSM(kf, im->smem_step1); }
+    { auto kf = k_step1<4, 256, 2>; SETSM(kf, im->smem_step1); }
     SETSM(k_step1<1>, im->smem_step1); SETSM(k_step1<2>, im->smem_step1); SETSM(k_step1<4>, im->smem_step1); SETSM(k_step1<8>, im->smem_step1);
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
@@ -431,7 +433,8 @@ void Engine::launch_fused(long long nsteps) {
         case 1: AIO_LAUNCH(k_step1<1>, ncol, NT, im->smem_step1, im->stream, p); break;
         case 2: AIO_LAUNCH(k_step1<2>, ncol, NT, im->smem_step1, im->stream, p); break;
         case 4:
-            if (NT == 256) { auto kf = k_step1<4, 256>; AIO_LAUNCH(kf, ncol, NT, im->smem_step1, im->stream, p); }
+            if (NT == 256 && im->step1_ctas == 2) { auto kf = k_step1<4, 256, 2>; AIO_LAUNCH(kf, ncol, NT, im->smem_step1, im->stream, p); }
+            else if (NT == 256) { auto kf = k_step1<4, 256>; AIO_LAUNCH(kf, ncol, NT, im->smem_step1, im->stream, p); }
             else AIO_LAUNCH(k_step1<4>, ncol, NT, im->smem_step1, im->stream, p);
             break;
         default: AIO_LAUNCH(k_step1<8>, ncol, NT, im->smem_step1, im->stream, p); break;
@@ -502,6 +505,14 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         if (value == "smem") im->full_reg = false;
         else if (value == "reg") im->full_reg = true;
         else throw std::invalid_argument("option full_lu: expected 'reg' or 'smem'");
+    } else if (key == "step1_ctas") {
+        if (value != "2" && value != "3") throw std::invalid_argument("option step1_ctas: expected 2 or 3");
+        im->step1_ctas = std::stoi(value);
+    } else if (key == "carveout") {          // shared-memory share of the SM's L1/shared storage for the fused kernel, in percent
+        const int pct = std::stoi(value);
+        if (pct < 0 || pct > 100) throw std::invalid_argument("option carveout: expected 0..100");
+        { auto kf = k_step1<4, 256>; CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); }
+        { auto kf = k_step1<4, 256, 2>; CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); }
     } else if (key == "fused") {
         if (value == "0") im->fused = false;
         else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");

@@ -50,5 +50,6 @@ private:
 
 // Per-species output / diagnostic files in the reference's column layout (io.cpp:704-932).
 void write_outputs(Engine& eng, const Problem& prob, int col, int index, const std::string& outdir);
+void write_monitor(Engine& eng, const Problem& prob, int col, const std::string& outdir, bool truncate, std::vector<double>& prev);
 
 }  // namespace aio

@@ -59,42 +59,43 @@ void hook_boundary_host(HookHost& h, int side) {
 }
 
 // Device side: called by the one thread that fills a column's ghost cells (apply_boundary_left/right, hydro.cuh) with the
-// shared boundary window W: cells 0..2ng-1 (left) or N2-2ng..N2-1 (right).
-__device__ __noinline__ void hook_boundary(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, int side) {
-    // the two sides are filled concurrently by different threads: each call copies, exposes and writes back only its own half
-    const int ng = p.ng, nw = 4 * ng, half = 2 * ng, off = side ? half : 0;
+// shared boundary window: cells 0..2ng-1 (left) or N2-2ng..N2-1 (right).  The two sides are filled concurrently by different
+// threads: each call copies, exposes and writes back only its own half.
+__device__ __noinline__ void hook_boundary(HookArgs a) {
+    const int ng = a.ng, nw = 4 * ng, half = 2 * ng, off = a.side ? half : 0;
     ::AOS cells[4]; ::AOS_prim prims[4];
     int err = 0;
-    for (int k = 0; k < half; k++) cells[k] = ::AOS(W.w[0 * nw + off + k], W.w[1 * nw + off + k], W.w[2 * nw + off + k]);
+    double* w = a.win;
+    for (int k = 0; k < half; k++) cells[k] = ::AOS(w[0 * nw + off + k], w[1 * nw + off + k], w[2 * nw + off + k]);
     c_Sim sim; EOS_Base eos; c_Species sp;
-    const long n = p.N2;
-    sim.num_cells = p.N; sim.num_ghosts = ng; sim.num_species = p.S; sim.num_bands_in = p.Bin; sim.num_bands_out = p.Bout;
-    sim.planet_mass = p.planet_mass; sim.planet_semimajor = p.planet_semimajor; sim.star_mass = p.star_mass;
-    sim.T_star = p.T_star; sim.R_star = p.R_star; sim.UV_star = p.UV_star; sim.X_star = p.X_star;
-    sim.domain_min = p.domain_min; sim.domain_max = p.domain_max;
-    sim.globalTime = p.cs[col].t; sim.dt = p.cs[col].dt; sim.steps = p.cs[col].steps;
-    sim.phi = {p.phi + idx_c(p, col, 0), n};
-    sim.x_i = {const_cast<double*>(p.x_i), n}; sim.x_i12 = {const_cast<double*>(p.x_i12), n};
-    sim.x_iVC = {const_cast<double*>(p.x_iVC), n}; sim.dx = {const_cast<double*>(p.dx), n};
-    sim.surf = {const_cast<double*>(p.surf), n}; sim.vol = {const_cast<double*>(p.vol), n};
-    eos._gamma_m1 = sc.gm1; eos._cv = sc.cv; eos._mass = sc.mass;
-    sp.base = &sim; sp.eos = &eos; sp.num_cells = p.N; sp.this_species_index = s; sp.is_dust_like = sc.is_dust_like;
-    sp.mass_amu = sc.mass_amu; sp.inv_mass = sc.inv_mass; sp.initial_fraction = sc.initial_fraction;
-    sp.density_excess = sc.density_excess; sp.static_charge = sc.static_charge; sp.cv = sc.cv;
-    sp.gamma_adiabat = sc.gamma_adiabat; sp.degrees_of_freedom = sc.degrees_of_freedom;
-    sp.const_T_space = sc.const_T_space; sp.const_opacity = sc.const_opacity;
+    const long n = a.N2;
+    sim.num_cells = a.N; sim.num_ghosts = ng; sim.num_species = a.S; sim.num_bands_in = a.Bin; sim.num_bands_out = a.Bout;
+    sim.planet_mass = a.planet_mass; sim.planet_semimajor = a.planet_semimajor; sim.star_mass = a.star_mass;
+    sim.T_star = a.T_star; sim.R_star = a.R_star; sim.UV_star = a.UV_star; sim.X_star = a.X_star;
+    sim.domain_min = a.domain_min; sim.domain_max = a.domain_max;
+    sim.globalTime = a.cs->t; sim.dt = a.cs->dt; sim.steps = a.cs->steps;
+    sim.phi = {a.phi, n};
+    sim.x_i = {const_cast<double*>(a.x_i), n}; sim.x_i12 = {const_cast<double*>(a.x_i12), n};
+    sim.x_iVC = {const_cast<double*>(a.x_iVC), n}; sim.dx = {const_cast<double*>(a.dx), n};
+    sim.surf = {const_cast<double*>(a.surf), n}; sim.vol = {const_cast<double*>(a.vol), n};
+    eos._gamma_m1 = a.gm1; eos._cv = a.cv; eos._mass = a.mass;
+    sp.base = &sim; sp.eos = &eos; sp.num_cells = a.N; sp.this_species_index = a.s; sp.is_dust_like = a.is_dust_like;
+    sp.mass_amu = a.mass_amu; sp.inv_mass = a.inv_mass; sp.initial_fraction = a.initial_fraction;
+    sp.density_excess = a.density_excess; sp.static_charge = a.static_charge; sp.cv = a.cv;
+    sp.gamma_adiabat = a.gamma_adiabat; sp.degrees_of_freedom = a.degrees_of_freedom;
+    sp.const_T_space = a.const_T_space; sp.const_opacity = a.const_opacity;
     std::vector<AOS> view;
     view.p = cells; view.n = n; view.err = &err;
-    if (side == 0) { view.nlo = half; view.hi0 = n; view.shift = 0; }             // cells 0 .. 2ng-1
+    if (a.side == 0) { view.nlo = half; view.hi0 = n; view.shift = 0; }           // cells 0 .. 2ng-1
     else { view.nlo = 0; view.hi0 = n - half; view.shift = n - half; }            // cells N2-2ng .. N2-1
     sp.u = view;
     sp.prim.p = prims; sp.prim.n = n; sp.prim.err = &err; sp.prim.nlo = view.nlo; sp.prim.hi0 = view.hi0; sp.prim.shift = view.shift;
     for (int k = 0; k < half; k++) { eos.compute_primitive(&cells[k], &prims[k], 1); eos.compute_auxillary(&prims[k], 1); }
-    if (side == 0) sp.user_boundary_left(view); else sp.user_boundary_right(sp.u);
     // user_boundary_right of the shipped plugins ignores its argument and writes the member `u` (cross_over.cpp:23-29):
     // both name the same window here
-    for (int k = 0; k < half; k++) { W.w[0 * nw + off + k] = cells[k].u1; W.w[1 * nw + off + k] = cells[k].u2; W.w[2 * nw + off + k] = cells[k].u3; }
-    if (err) { p.cs[col].status = COL_HOOK_RANGE; p.cs[col].t = 1.1 * p.cs[col].t_max; }
+    if (a.side == 0) sp.user_boundary_left(view); else sp.user_boundary_right(sp.u);
+    for (int k = 0; k < half; k++) { w[0 * nw + off + k] = cells[k].u1; w[1 * nw + off + k] = cells[k].u2; w[2 * nw + off + k] = cells[k].u3; }
+    if (err) { a.cs->status = COL_HOOK_RANGE; a.cs->t = 1.1 * a.cs->t_max; }
 }
 
 }  // namespace aio

@@ -108,8 +108,32 @@ struct BndWin {
 };
 
 #ifdef AIO_PROBLEM_FILE
-// defined in hooks_glue.inl (end of engine.cu), next to the problem file it wraps
-__device__ void hook_boundary(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, int side);
+// What a boundary hook can see, passed BY VALUE to the out-of-line glue (hooks_glue.inl, end of engine.cu): taking the address
+// of the kernel parameter block would force a local copy of all of DevParams in every hydro kernel.
+struct HookArgs {
+    int N, N2, ng, S, Bin, Bout, col, s, side, is_dust_like;
+    double planet_mass, planet_semimajor, star_mass, T_star, R_star, UV_star, X_star, domain_min, domain_max;
+    double gm1, cv, mass, mass_amu, inv_mass, initial_fraction, density_excess, static_charge, gamma_adiabat, degrees_of_freedom;
+    double const_T_space, const_opacity;
+    double* phi; const double *x_i, *x_i12, *x_iVC, *dx, *surf, *vol;
+    ColState* cs;
+    double* win;                 // this side's half of the boundary window: [3][4*ng], see BndWin
+};
+__device__ void hook_boundary(HookArgs a);
+__device__ __forceinline__ void call_hook(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, int side) {
+    HookArgs a;
+    a.N = p.N; a.N2 = p.N2; a.ng = p.ng; a.S = p.S; a.Bin = p.Bin; a.Bout = p.Bout; a.col = col; a.s = s; a.side = side;
+    a.is_dust_like = sc.is_dust_like;
+    a.planet_mass = p.planet_mass; a.planet_semimajor = p.planet_semimajor; a.star_mass = p.star_mass; a.T_star = p.T_star;
+    a.R_star = p.R_star; a.UV_star = p.UV_star; a.X_star = p.X_star; a.domain_min = p.domain_min; a.domain_max = p.domain_max;
+    a.gm1 = sc.gm1; a.cv = sc.cv; a.mass = sc.mass; a.mass_amu = sc.mass_amu; a.inv_mass = sc.inv_mass;
+    a.initial_fraction = sc.initial_fraction; a.density_excess = sc.density_excess; a.static_charge = sc.static_charge;
+    a.gamma_adiabat = sc.gamma_adiabat; a.degrees_of_freedom = sc.degrees_of_freedom;
+    a.const_T_space = sc.const_T_space; a.const_opacity = sc.const_opacity;
+    a.phi = p.phi + idx_c(p, col, 0); a.x_i = p.x_i; a.x_i12 = p.x_i12; a.x_iVC = p.x_iVC; a.dx = p.dx; a.surf = p.surf; a.vol = p.vol;
+    a.cs = p.cs + col; a.win = W.w;
+    hook_boundary(a);
+}
 #endif
 
 __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, double prim2_speed) {
@@ -157,7 +181,7 @@ __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesCons
         break; }
     default:         // 0 = user hook (problem plugin); the stock library rejects such decks at create time
 #ifdef AIO_PROBLEM_FILE
-        if (sc.bc_left == 0) hook_boundary(p, sc, col, s, W, 0);
+        if (sc.bc_left == 0) call_hook(p, sc, col, s, W, 0);
 #endif
         break;
     }
@@ -212,7 +236,7 @@ __device__ inline void apply_boundary_right(const DevParams& p, const SpeciesCon
         break;
     default:
 #ifdef AIO_PROBLEM_FILE
-        if (sc.bc_right == 0) hook_boundary(p, sc, col, s, W, 1);
+        if (sc.bc_right == 0) call_hook(p, sc, col, s, W, 1);
 #endif
         break;
     }

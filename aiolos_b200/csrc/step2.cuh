@@ -941,8 +941,8 @@ __global__ void __launch_bounds__(256, 3) k_rad3(DevParams p) {
 // One CTA advances its column by up to `p.steps_per_launch` time steps: step head -> both hydro stages -> [radiation] -> step
 // tail, with the conserved state in registers and the column's clock (ColState) in shared memory for the whole launch.  HBM sees
 // u once per launch instead of four times per step; J, primlast and the static tables are re-read through L2.
-template <int CPT, int NTC = 0>
-__global__ void __launch_bounds__(256, AIO_STEP1_MINB) k_step1(DevParams p) {
+template <int CPT, int NTC = 0, int MINB = AIO_STEP1_MINB>
+__global__ void __launch_bounds__(256, MINB) k_step1(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     __shared__ ColState s_cs;
     __shared__ double s_p2v;

@@ -1,7 +1,7 @@
 // Output files in the reference's layout (io.cpp:704-778 per-species output, io.cpp:787-932 diagnostic file): same file names,
 // `setprecision(15)`, tab separators, ghost rows with '-' placeholders (23 tokens) and 24-column interior rows, so that the
 // reference's python checkers (test_files/load_aiolos.py) read them unchanged.  Runs on the host from a downloaded column;
-// it is off the time-step path.
+// it is off the time-step path.  write_monitor() adds one row to monitor_<stem>.dat (io.cpp:939-1072).
 //
 // Columns of output_<stem>_<species>_t<k>.dat (1-based): 1 x_i12, 2-4 u1 u2 u3, 5-7 flux, 8-10 balance, 11 pres, 12 u2/u1,
 // 13 T, 14 c_s/dx, 15 cflfactor/(|v|/dx), 16 c_s, 17 dt_dE, 18 u_analytic, 19 alpha_01, 20 phi_s, 21 M_enc, 22 -dG+dGdT*T,
@@ -158,6 +158,58 @@ void write_outputs(Engine& eng, const Problem& q, int col, int index, const std:
             out << std::endl;
         }
     }
+}
+
+// One row of monitor_<stem>.dat (io.cpp:939-1072): time, dt, then quantities sampled in cell 5 (and c_v T of cell 1), all with
+// setprecision(24).  `prev` carries previous_monitor_J / previous_monitor_T (B_out + S entries, zero before the first row as in
+// init_and_bounds.cpp:758-759, so the first row's convergence columns are inf/nan exactly like the reference's).
+// truncate != 0 starts a new file (the reference does that when steps == 0).
+void write_monitor(Engine& eng, const Problem& q, int col, const std::string& outdir, bool truncate, std::vector<double>& prev) {
+    const int N2 = q.num_cells + 2, S = q.num_species, Bout = q.num_bands_out;
+    const double c_light = 2.99792458e10, pi = 3.141592653589793, sigma_rad = 5.670374419e-5;
+    if (N2 < 6) throw std::invalid_argument("write_monitor: fewer than 6 array entries");
+    if ((int)prev.size() != Bout + S) prev.assign(Bout + S, 0.0);
+    const std::string dir = outdir.empty() ? q.workingdir : outdir;
+    const std::string name = dir + "monitor_" + stem_of(q.simname) + ".dat";
+    double t = 0, dt = 0; long long steps = 0; int state = 0;
+    eng.status(col, &t, &dt, &steps, &state);
+    std::vector<double> buf(N2), J5(Bout, 0.), v5(S), rho5(S), T5(S), cs5(S), T1(S);
+    for (int b = 0; b < Bout; b++) { eng.get_field(col, 0, 16 + b, buf.data(), N2); J5[b] = buf[5]; }
+    for (int s = 0; s < S; s++) {
+        std::vector<double> u1(N2), u2(N2), u3(N2);
+        eng.get_field(col, s, 0, u1.data(), N2); eng.get_field(col, s, 1, u2.data(), N2); eng.get_field(col, s, 2, u3.data(), N2);
+        const SpeciesData& d = q.species[s];
+        const double gm1 = 2. / d.degrees_of_freedom;
+        auto temperature = [&](int i, double* cs) {        // eos.cpp:19-63
+            const double v = u2[i] / u1[i], p = gm1 * (u3[i] - 0.5 * u2[i] * v), e = (p / u1[i]) / gm1;
+            if (cs) *cs = std::sqrt((gm1 + 1) * gm1 * e);
+            return e / d.cv;
+        };
+        v5[s] = u2[5] / u1[5]; rho5[s] = u1[5]; T5[s] = temperature(5, &cs5[s]); T1[s] = temperature(1, nullptr);
+    }
+    std::ofstream f(name, truncate ? std::ios_base::trunc : std::ios_base::app);
+    if (!f.is_open()) throw std::runtime_error("cannot open " + name);
+    f << std::setprecision(24);
+    f << t << '\t' << dt << '\t';
+    for (int s = 0; s < S; s++) f << v5[s] << '\t';
+    double erad = 0;
+    for (int b = 0; b < Bout; b++) erad += J5[b] * 4 * pi / c_light;
+    f << erad << '\t';
+    double eint = 0;
+    for (int s = 0; s < S; s++) eint += rho5[s] * q.species[s].cv * T5[s];
+    f << eint << '\t';
+    f << std::pow(c_light * erad / sigma_rad / 4., 0.25) << '\t';
+    for (int s = 0; s < S; s++) f << T5[s] << '\t';
+    for (int s = 0; s < S; s++) f << cs5[s] / q.dx[5] << '\t';
+    for (int b = 0; b < Bout; b++) f << J5[b] * 4 * pi / c_light << '\t';
+    for (int b = 0; b < Bout; b++) { f << ((J5[b] - prev[b]) / prev[b]) << '\t'; prev[b] = J5[b]; }
+    for (int s = 0; s < S; s++) {
+        const double B = sigma_rad / pi * std::pow(T5[s], 4.);
+        f << ((B - prev[Bout + s]) / prev[Bout + s]) << '\t';
+        prev[Bout + s] = B;
+    }
+    for (int s = 0; s < S; s++) f << q.species[s].cv * T1[s] << '\t';
+    f << std::endl;
 }
 
 }  // namespace aio

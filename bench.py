@@ -147,7 +147,8 @@ def main():
                                                               "1e-20 s and reaches the CFL regime after ~450 steps")
     ap.add_argument("--ref-steps", type=int, default=4000, help="time steps per column per bench step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="aio_set_option pairs (kernel variants)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,6 +185,8 @@ def main():
     finally:
         os.chdir(cwd)
     N, S = ens.num_cells, ens.num_species
+    for kv in args.opt:
+        ens.set_option(*kv.split("=", 1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -292,6 +295,8 @@ def main():
                 "cpu_baseline": cpu}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
+        if args.opt:
+            line["config"]["options"] = args.opt
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if dist:

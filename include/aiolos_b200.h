@@ -11,6 +11,7 @@
  *   aio_get               public members c_Species::u / prim / dS, c_Sim::Jrad_FLD / phi   aiolos.h:533-670,881-957
  *   aio_upload_state / aio_download_state   std::vector<AOS> c_Species::u for all columns (host buffers; end-to-end path)
  *   aio_write_outputs     c_Species::print_AOS_component_tofile + c_Sim::print_diagnostic_file   io.cpp:704-932
+ *   aio_write_monitor     c_Sim::print_monitor                                                  io.cpp:939-1072
  * The problems/<name>.cpp hook API (aiolos.h:1050-1055) is described in INTEGRATION.md.
  */
 #ifndef AIOLOS_B200_H
@@ -102,6 +103,9 @@ int aio_commit_upload(aio_ensemble* e);
 int aio_column_mass(aio_ensemble* e, double* mass_per_column);
 
 int aio_write_outputs(aio_ensemble* e, int column, int index, const char* outdir);
+/* c_Sim::print_monitor (io.cpp:939-1072): append one row for this column's current state to <outdir>monitor_<stem>.dat
+ * (outdir NULL/"" = the deck directory); truncate != 0 starts a new file, as the reference does at step 0. */
+int aio_write_monitor(aio_ensemble* e, int column, const char* outdir, int truncate);
 
 long long aio_kernel_launches(aio_ensemble* e);
 long long aio_total_steps(aio_ensemble* e);      /* sum over columns of completed steps */

@@ -112,7 +112,7 @@ typedef struct { double t; }* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMultiProcessorCount = 16,
-       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }

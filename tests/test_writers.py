@@ -64,3 +64,32 @@ def test_output_files_match_reference(emu_lib, ref_run, tmp_path, par, species, 
     # x, J_tot, S_tot, J_b, S_b (2), dS_b (2), rho*kappa_R, dtau, tau_in (2), kappa_S (2*S), kappa_P (S), kappa_R (S), T_rad, T_s, p
     cols = [c for c in range(ncol - Bout)]          # all but the fluxes F_b (differences of nearly equal J: compared loosely)
     _cmp(mine, ref, cols, 1e-6, "diagnostic")
+
+
+@pytest.mark.parametrize("par,S", [("dynamic3_euv1e3_C_1s2b_rerun.par", 1), ("dynamic3_2spc_collheat.par", 2)])
+def test_monitor_row_matches_reference(emu_lib, ref_run, tmp_path, par, S, monkeypatch):
+    """c_Sim::print_monitor (io.cpp:939-1072): the row the reference appends at the end of its run against ours for the same
+    state.  The convergence columns depend on the previous row and are checked for structure only."""
+    monkeypatch.chdir(ref_run)
+    ens = A.Ensemble.from_files("runs_mdot_vs_euv_plot/", par, "", lib=emu_lib)
+    ens.advance(700)
+    out = str(tmp_path) + "/"
+    ens.write_monitor(0, out, truncate=True)
+    ens.write_monitor(0, out)                                   # second row: convergence columns are now finite (0)
+    stem = par[:-4]
+    mine = _rows(os.path.join(out, f"monitor_{stem}.dat"))
+    ref = _rows(os.path.join(ref_run, "runs_mdot_vs_euv_plot", f"monitor_{stem}.dat"))
+    assert len(mine) == 2 and len(mine[0]) == len(ref[-1]) == len(mine[1])
+    Bout = 1
+    ncol = 2 + S + 3 + S + S + Bout + Bout + S + S
+    assert len([v for v in ref[-1] if v != ""]) == ncol
+    a = np.array([float(v) for v in mine[0][:ncol]]); b = np.array([float(v) for v in ref[-1][:ncol]])
+    conv = list(range(5 + 3 * S + Bout, 5 + 4 * S + 2 * Bout))
+    speed = list(range(2, 2 + S))                               # prim[5].speed: ~1e-9 cm/s of noise in the hydrostatic layers, printed by the
+                                                                # reference from the primitives its last hydro stage saw
+    cs = list(range(5 + 2 * S, 5 + 3 * S))                      # prim.sound_speed is the pre-radiation value in the reference
+    strict = [c for c in range(ncol) if c not in conv + speed + cs]
+    assert np.all(np.abs(a[strict] - b[strict]) <= 1e-7 * np.abs(b[strict])), (a, b)
+    assert np.all(np.abs(a[cs] - b[cs]) <= 2e-2 * np.abs(b[cs]))
+    second = np.array([float(v) for v in mine[1][:ncol]])
+    assert np.all(second[conv] == 0.0) and np.all(~np.isfinite(a[conv]))      # first row divides by the zero-initialised memory
