@@ -76,6 +76,8 @@ struct DevParams {
     int closed_radiative_boundaries, use_planetary_temperature, couple_J_into_T, solve_for_j;
     int radiation_matter_equilibrium_test, use_total_pressure, collision_model, opacity_model;
     int use_avg_temperature, update_coll_frequently;
+    int do_hydrodynamics;       // DO_HYDRO; 0 = no hydro stages until t > start_hydro_time (advection.cpp:62-64,139,170-200)
+    double start_hydro_time;
     double avg_temperature_t0, avg_temperature_t1;
     int last_kernel;            // 0 hydro, 1 friction, 2 radiation: who runs the step tail
     int tridiag_serial;         // 1: scalar J system solved in the reference's Thomas order on one lane (validation mode)
@@ -119,6 +121,8 @@ struct DevParams {
     double *prim2v;                     // [ncol][S]  prim[2].speed as last computed (fixed BC, init_and_bounds.cpp:1856)
     const double *solar_heating_final;  // [ncol][Bin]
     ColState* cs;                       // [ncol]
+    // long columns (or many species): the per-column work arrays of the v1 kernels live in HBM instead of shared memory
+    double* scratch; size_t scratch_stride; int scratch_hydro, scratch_rad;
     int steps_per_launch;               // fused persistent kernel (k_step1): time steps one launch may advance a column
     long long step_limit;               // columns stop when steps reaches this
 };
@@ -140,6 +144,12 @@ __host__ __device__ inline size_t idx_J(const DevParams& p, int col, int b, int 
 // the outermost entry num_cells+1 and the entries 0, 1 keep the boundary condition's value.
 __device__ __forceinline__ double phi_snapshot(const DevParams& p, int col, const double* phi, int j) {
     return (j == p.N) ? p.phiN[col] : phi[j];
+}
+
+// Is the hydrodynamics module on for the step that starts at time t?  (advection.cpp:62-64: the switch flips, for good, once
+// globalTime has passed START_HYDRO_TIME; t is monotonic, so the comparison alone reproduces the sticky flag.)
+__device__ __forceinline__ bool hydro_on(const DevParams& p, double t) {
+    return p.do_hydrodynamics != 0 || (p.start_hydro_time > 0. && t > p.start_hydro_time);
 }
 
 // physical constants, verbatim values of aiolos.h:47-77

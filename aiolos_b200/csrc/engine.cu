@@ -29,6 +29,8 @@ struct Engine::Impl {
     size_t smem_hydro = 0, smem_rad = 0, smem_fric = 0;
     int nt_full = 0; size_t smem_full = 0;
     bool has_friction = false;
+    bool big = false;               // 1024 threads per column and/or work arrays in HBM (long columns): v1 kernels only
+    bool hydro_switch = false;      // deck runs (part of) its time with the hydro module off
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
     size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
     bool full_reg = false;          // register-resident LU: measured slower (instruction-cache bound, profiles/r1g); option full_lu=reg
@@ -84,7 +86,6 @@ static void check_supported(const Problem& q) {
     if (q.num_species < 1 || q.num_species > MAXS) fail("num_species outside 1.." + std::to_string(MAXS));
     if (q.num_bands_in > MAXB || q.num_bands_out > MAXB) fail("more than 32 radiation bands");
     if (q.num_cells < 6) fail("fewer than 6 cells");
-    if (!q.do_hydrodynamics || q.start_hydro_time > 0) fail("DO_HYDRO 0 / START_HYDRO_TIME");
     if (q.use_self_gravity) fail("PARI_SELF_GRAV_SWITCH 1");
     if (q.rs_time > 0) fail("PARI_SMOOTHING_TIME > 0 (time-dependent potential)");
     if (q.K_zz_init != 0) fail("KZZ_INIT != 0");
@@ -99,7 +100,9 @@ static void check_supported(const Problem& q) {
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && q.num_species > 8) fail("simple FLD + collisional heating with more than 8 species");
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && !q.update_coll_frequently) fail("UPDATE_COLL_FREQUENTLY 0");
     if (q.use_rad_fluxes && std::string("CPTKD").find(q.opacity_model) == std::string::npos) fail(std::string("opacity model ") + q.opacity_model);
-    if (q.num_species > 1 && q.friction_solver == 0) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
+    // the analytic 2/3-species drag solver is not built; with hydro off for the whole run the reference never calls it
+    // (advection.cpp:208-212: compute_drag_update only if do_hydrodynamics or friction_solver > 0)
+    if (q.num_species > 1 && q.friction_solver == 0 && (q.do_hydrodynamics || q.start_hydro_time > 0)) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
     if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
     for (auto& sp : q.species) {
         if ((sp.boundary_left == 0 || sp.boundary_right == 0) && !hooks_compiled())
@@ -128,6 +131,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.N = N; p.N2 = N2; p.NP = NP; p.S = S; p.Bin = q0.num_bands_in; p.Bout = q0.num_bands_out; p.ng = q0.num_ghosts; p.ncol = ncol;
     p.order = q0.order; p.geometry = q0.geometry; p.problem_number = q0.problem_number;
     p.use_rad_fluxes = q0.use_rad_fluxes; p.friction_solver = q0.friction_solver;
+    p.do_hydrodynamics = q0.do_hydrodynamics; p.start_hydro_time = q0.start_hydro_time;
     p.use_collisional_heating = q0.use_collisional_heating; p.photochemistry_level = q0.photochemistry_level;
     p.closed_radiative_boundaries = q0.closed_radiative_boundaries; p.use_planetary_temperature = q0.use_planetary_temperature;
     p.couple_J_into_T = q0.couple_J_into_T; p.solve_for_j = q0.solve_for_j;
@@ -135,7 +139,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.collision_model = q0.collision_model; p.opacity_model = q0.opacity_model;
     p.use_avg_temperature = q0.use_avg_temperature; p.update_coll_frequently = q0.update_coll_frequently;
     p.avg_temperature_t0 = q0.avg_temperature_t0; p.avg_temperature_t1 = q0.avg_temperature_t1;
-    im->has_friction = (q0.friction_solver >= 0 && S > 1);     // compute_drag_update, source.cpp:233-243
+    im->has_friction = (q0.friction_solver > 0 && S > 1);      // compute_drag_update, source.cpp:233-243 (solver 0 is rejected above
+                                                               // unless hydro stays off, in which case nothing is called)
     p.last_kernel = q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
     p.max_timestep_change = q0.max_timestep_change; p.dt_min_init = q0.dt_min_init; p.dt_max = q0.dt_max;
     p.energy_epsilon = q0.energy_epsilon; p.CFL_break_time = q0.CFL_break_time;
@@ -290,8 +295,9 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     int NT = 256;
     if (N2 <= 32) NT = 32; else if (N2 <= 64) NT = 64; else if (N2 <= 128) NT = 128;
     int CPT = (N2 + NT - 1) / NT;
-    if (CPT > 8) throw std::runtime_error("unsupported configuration: more than 2046 cells per column");
-    if (CPT == 3) CPT = 4; if (CPT > 4) CPT = 8;
+    if (CPT > 8) { NT = (N2 <= 4096) ? 512 : 1024; CPT = (N2 + NT - 1) / NT; }   // long columns: 512 / 1024 threads, v1 kernels
+    if (CPT > 8) throw std::runtime_error("unsupported configuration: more than 8190 cells per column");
+    if (CPT == 3) CPT = 4; if (CPT > 4 || NT > 256) CPT = 8;
     im->NT = NT; im->CPT = CPT;
     im->smem_hydro = ((size_t)9 * N2 + 32 + 12 * p.ng) * sizeof(double);
     im->smem_rad = ((size_t)(5 * S + 7) * N2 + 32) * sizeof(double);
@@ -301,21 +307,42 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->smem_step1 = ((size_t)9 * NT * CPT + 32 + 12 * p.ng + 64) * sizeof(double);
     im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
     for (auto& sp : q0.species) if (sp.boundary_left == 0 || sp.boundary_right == 0) im->fused = false;   // hooks flag errors through p.cs
+    im->hydro_switch = (!q0.do_hydrodynamics || q0.start_hydro_time > 0);
+    if (im->hydro_switch) { im->v2 = false; im->fused = false; }   // DO_HYDRO 0 / START_HYDRO_TIME: only the v1 kernels carry the switch
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (im->smem_hydro > (size_t)maxsm || (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm))
-        throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
+    // work arrays that do not fit in one CTA's shared memory (long columns, or many species in the simple FLD kernel) go to HBM
+    p.scratch = nullptr; p.scratch_stride = 0; p.scratch_hydro = p.scratch_rad = 0;
+    {
+        size_t need = 0;
+        if (im->smem_hydro > (size_t)maxsm) { p.scratch_hydro = 1; need = std::max(need, im->smem_hydro / sizeof(double)); im->smem_hydro = 0; }
+        if (p.use_rad_fluxes == 2 && im->smem_rad > (size_t)maxsm) { p.scratch_rad = 1; need = std::max(need, im->smem_rad / sizeof(double)); im->smem_rad = 0; }
+        if (need) {
+            p.scratch_stride = (need + 31) / 32 * 32;
+            p.scratch = im->dalloc<double>((size_t)ncol * p.scratch_stride);
+        }
+    }
+    im->big = (NT > 256) || p.scratch != nullptr;
+    if (im->big) { im->v2 = false; im->fused = false; }            // only the v1 kernels take 1024 threads / HBM work arrays
 #define SETSM(K, B) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B)))
     SETSM(k_hydro<1>, im->smem_hydro); SETSM(k_hydro<2>, im->smem_hydro); SETSM(k_hydro<4>, im->smem_hydro); SETSM(k_hydro<8>, im->smem_hydro);
+    { auto k5 = k_hydro<8, 512>; auto k8 = k_hydro<8, 1024>; SETSM(k5, im->smem_hydro); SETSM(k8, im->smem_hydro); }
+    if (!im->big) {
     { auto kf = k_step1<4, 256>; SETSM(kf, im->smem_step1); }
     { auto kf = k_step1<4, 256, 2>; SETSM(kf, im->smem_step1); }
     SETSM(k_step1<1>, im->smem_step1); SETSM(k_step1<2>, im->smem_step1); SETSM(k_step1<4>, im->smem_step1); SETSM(k_step1<8>, im->smem_step1);
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
-        if (im->smem_rad2 > (size_t)maxsm) throw std::runtime_error("unsupported configuration: column does not fit in shared memory");
-        SETSM(k_rad3<1>, im->smem_rad3); SETSM(k_rad3<2>, im->smem_rad3); SETSM(k_rad3<4>, im->smem_rad3); SETSM(k_rad3<8>, im->smem_rad3);
-        SETSM(k_rad2<1>, im->smem_rad2); SETSM(k_rad2<2>, im->smem_rad2); SETSM(k_rad2<4>, im->smem_rad2); SETSM(k_rad2<8>, im->smem_rad2);
+        if (im->smem_rad2 > (size_t)maxsm) { im->v2 = false; im->fused = false; }
+        else {
+            SETSM(k_rad3<1>, im->smem_rad3); SETSM(k_rad3<2>, im->smem_rad3); SETSM(k_rad3<4>, im->smem_rad3); SETSM(k_rad3<8>, im->smem_rad3);
+            SETSM(k_rad2<1>, im->smem_rad2); SETSM(k_rad2<2>, im->smem_rad2); SETSM(k_rad2<4>, im->smem_rad2); SETSM(k_rad2<8>, im->smem_rad2);
+        }
     }
-    if (p.use_rad_fluxes == 2) { SETSM(k_rad_simple<1>, im->smem_rad); SETSM(k_rad_simple<2>, im->smem_rad); SETSM(k_rad_simple<4>, im->smem_rad); SETSM(k_rad_simple<8>, im->smem_rad); }
+    }
+    if (p.use_rad_fluxes == 2) {
+        SETSM(k_rad_simple<1>, im->smem_rad); SETSM(k_rad_simple<2>, im->smem_rad); SETSM(k_rad_simple<4>, im->smem_rad); SETSM(k_rad_simple<8>, im->smem_rad);
+        { auto k5 = k_rad_simple<8, 512>; auto k8 = k_rad_simple<8, 1024>; SETSM(k5, im->smem_rad); SETSM(k8, im->smem_rad); }
+    }
 #undef SETSM
     AIO_LAUNCH(k_prime, ncol, 256, 0, im->stream, p);
     CK(cudaGetLastError());
@@ -355,6 +382,9 @@ void Engine::launch_step() {
         case 4: AIO_LAUNCH(k_hydro2<4>, ncol, NT, im->smem_hydro, im->stream, p); break;
         default: AIO_LAUNCH(k_hydro2<8>, ncol, NT, im->smem_hydro, im->stream, p); break;
         }
+    } else if (NT > 256) {               // long columns: CPT is 8 by construction (N2 > 8 * 256)
+        if (NT == 512) { auto k = k_hydro<8, 512>; AIO_LAUNCH(k, ncol, NT, im->smem_hydro, im->stream, p); }
+        else { auto k = k_hydro<8, 1024>; AIO_LAUNCH(k, ncol, NT, im->smem_hydro, im->stream, p); }
     } else
     switch (im->CPT) {
     case 1: AIO_LAUNCH(k_hydro<1>, ncol, NT, im->smem_hydro, im->stream, p); break;
@@ -382,6 +412,10 @@ void Engine::launch_step() {
         case 4: AIO_LAUNCH(k_rad2<4>, ncol, NT, im->smem_rad2, im->stream, p); break;
         default: AIO_LAUNCH(k_rad2<8>, ncol, NT, im->smem_rad2, im->stream, p); break;
         }
+        im->launches++;
+    } else if (p.use_rad_fluxes == 2 && NT > 256) {
+        if (NT == 512) { auto k = k_rad_simple<8, 512>; AIO_LAUNCH(k, ncol, NT, im->smem_rad, im->stream, p); }
+        else { auto k = k_rad_simple<8, 1024>; AIO_LAUNCH(k, ncol, NT, im->smem_rad, im->stream, p); }
         im->launches++;
     } else if (p.use_rad_fluxes == 2) {
         switch (im->CPT) {
@@ -518,7 +552,7 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");
     } else if (key == "kernels") {
         if (value == "v1") im->v2 = false;
-        else if (value == "v2") im->v2 = true;
+        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME run the v1 kernels"); im->v2 = true; }
         else throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
         if (total_steps() != 0) throw std::invalid_argument("option kernels must be set before the first step");
     } else throw std::invalid_argument("unknown option '" + key + "'");

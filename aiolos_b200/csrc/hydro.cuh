@@ -248,7 +248,9 @@ __device__ inline double step_head_dt(const DevParams& p, ColState& c) {
     c.timestep_rad2 = c.dt / c.maxde * p.energy_epsilon;
     if (c.t > p.CFL_break_time) c.cflfactor = 0.9;
     c.cfl_step = c.cflfactor / c.minstep;
-    double dt = smin(c.cfl_step, c.dt * p.max_timestep_change);
+    double dt;
+    if (hydro_on(p, c.t)) dt = smin(c.cfl_step, c.dt * p.max_timestep_change);
+    else dt = smin(smin(c.timestep_rad2, c.dt * p.max_timestep_change), p.dt_max);     // helpers.cpp:80-85
     dt = smin(dt, c.timestep_rad2);
     dt = smin(dt, c.t_max - c.t);
     if (c.steps == 0) dt = smin(dt, p.dt_min_init);
@@ -329,7 +331,10 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
             d1[k] = d2[k] = d3[k] = 0;
         }
         double prim2_speed = p.prim2v[(size_t)col * p.S + s];
-        const int nstage = (p.order == 2) ? 2 : 1;
+        // hydro off (DO_HYDRO 0, or START_HYDRO_TIME not reached): no stages; at second order the boundary conditions are still
+        // applied once (advection.cpp:196-200), at first order nothing happens before the final compute_pressure
+        const bool hyd = hydro_on(p, t_old);
+        const int nstage = hyd ? ((p.order == 2) ? 2 : 1) : ((p.order == 2) ? 1 : 0);
         for (int stage = 0; stage < nstage; stage++) {
             // ---- boundary conditions -------------------------------------------------------------------
 #pragma unroll
@@ -340,7 +345,7 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
             __syncthreads();
             if (tid == 0) {
                 apply_boundary_left(p, sc, col, s, W, prim2_speed);
-                if (sc.use_wave == 1) {                                         // init_and_bounds.cpp:1982-1987
+                if (sc.use_wave == 1 && hyd) {                                  // init_and_bounds.cpp:1982-1987
                     double tt = (stage == 0) ? t_old : t_old + dt;
                     W.at(1, 0) = W.at(0, 0) * sc.wave_amplitude * sin(12. * M_PI * tt / sc.wave_period);
                     W.at(1, 1) = W.at(1, 0);
@@ -353,6 +358,7 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
                 int j = tid + k * NT;
                 if (j < N2 && (j < 2 * ng || j >= N2 - 2 * ng)) { u1[k] = W.at(0, j); u2[k] = W.at(1, j); u3[k] = W.at(2, j); }
             }
+            if (!hyd) break;
             // ---- cons -> prim ----------------------------------------------------------------------------
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
@@ -482,10 +488,14 @@ __device__ __forceinline__ StepInfo step_head_on(const DevParams& p, ColState& c
 }
 __device__ __forceinline__ StepInfo step_head(const DevParams& p, const int col) { return step_head_on(p, p.cs[col]); }
 
-template <int CPT>
-__global__ void __launch_bounds__(256, 2) k_hydro(DevParams p) {
-    AIO_DYN_SMEM(double, sm);
+// NTB = largest block the instantiation is launched with: 256 (two CTAs per SM) for columns of up to 2046 cells, 1024 for longer
+// ones.  When the nine work arrays do not fit in shared memory they are taken from the column's HBM scratch area instead (the
+// code below only ever touches them between __syncthreads(), with plain loads and stores).
+template <int CPT, int NTB = 256>
+__global__ void __launch_bounds__(NTB, NTB == 256 ? 2 : 1) k_hydro(DevParams p) {
+    AIO_DYN_SMEM(double, sm_dyn);
     const int col = blockIdx.x;
+    double* sm = p.scratch_hydro ? p.scratch + (size_t)col * p.scratch_stride : sm_dyn;
     const StepInfo si = step_head(p, col);
     if (!si.active) return;
     TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;

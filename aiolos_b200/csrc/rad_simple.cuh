@@ -360,10 +360,11 @@ __device__ __forceinline__ void rad_simple_phase(const DevParams& p, const int c
     tail_commit(p, col, acc, red, negJ != 0, negJval);
 }
 
-template <int CPT>
-__global__ void __launch_bounds__(256, 2) k_rad_simple(DevParams p) {
-    AIO_DYN_SMEM(double, sm);
+template <int CPT, int NTB = 256>
+__global__ void __launch_bounds__(NTB, NTB == 256 ? 2 : 1) k_rad_simple(DevParams p) {
+    AIO_DYN_SMEM(double, sm_dyn);
     const int col = blockIdx.x;
+    double* sm = p.scratch_rad ? p.scratch + (size_t)col * p.scratch_stride : sm_dyn;     // see k_hydro
     const ColState& c = p.cs[col];
     if (!c.in_step) return;
     rad_simple_phase<CPT>(p, col, sm, c.dt, c.t);

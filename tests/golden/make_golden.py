@@ -42,6 +42,15 @@ CASES = {
     "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", None, [1, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
+    # DO_HYDRO 0: radiation-only relaxation (no hydro stages; at order 2 only the boundary conditions are applied,
+    # advection.cpp:196-200; dt from the energy limiter, helpers.cpp:80-85), full FLD
+    "n1_searth_nohydro": ("test2/", "SEarth_nohydro_1s1b.par", "mix_HHe.spc", [1, 100, 300]),
+    # the reference's cartesian radiation test, 12 cells, run to its t_max (242 steps)
+    "n2_radtest_1s1b": ("test2/", "cartesian_radiationtest_1spec1band.par", "mix_HHe.spc", [1, 100, 242]),
+    # a long column (3054 cells > the 2046 one 256-thread CTA holds in shared memory): 1024 threads per column, work arrays in HBM
+    "b1_hjwind_3054": ("runs_searth/", "hjwind_dgrey_1s1b.par", "mix3.spc", [100, 600]),
+    # configs[3] at three times its resolution (2987 cells; our variant): hydro + irradiation + simple FLD on a long column
+    "b2_dynamic3_3k": ("runs_mdot_vs_euv_plot/", "dynamic3_euv_3k.par", None, [100, 600]),
     # PBC_model/dusty_wind.par at 1000 instead of 4000 cells per decade (our variant), with the reference linked against its own
     # problems/dusty_wind.cpp (oracle/_ref/aiolos_ref_dump_dusty_wind): user initial conditions + user boundary hooks on both
     # sides, gas + dust, numeric friction, opacity model D, full FLD with 3x3 blocks

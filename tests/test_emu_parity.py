@@ -17,6 +17,8 @@ CASES = [
     ("c5_dynamic3_2spc_collheat", 1, 1e-10), ("c5_dynamic3_2spc_collheat", 100, 1e-8),
     ("c6_dynamic3_2spc_fullfld", 1, 1e-10), ("c6_dynamic3_2spc_fullfld", 100, 1e-8),
     ("d1_dustywave_nonstiff", 1, 1e-10), ("d1_dustywave_nonstiff", 100, 1e-8), ("d1_dustywave_nonstiff", 800, 1e-8),
+    ("n1_searth_nohydro", 1, 1e-10), ("n1_searth_nohydro", 100, 1e-8), ("n2_radtest_1s1b", 242, 1e-8),
+    ("b1_hjwind_3054", 100, 1e-8), ("b2_dynamic3_3k", 100, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8),
 ]
 
