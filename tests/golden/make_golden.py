@@ -55,6 +55,9 @@ CASES = {
     # problems/dusty_wind.cpp (oracle/_ref/aiolos_ref_dump_dusty_wind): user initial conditions + user boundary hooks on both
     # sides, gas + dust, numeric friction, opacity model D, full FLD with 3x3 blocks
     "p1_dusty_wind": ("PBC_model/", "dusty_wind_1k.par", "silicate.spc", [1, 20, 100, 1000], "dusty_wind"),
+    # the shipped deck itself, unmodified (4002 cells): plugin + long column; only the 300-step state is kept (no init dump:
+    # plugin decks are created from files)
+    "p2_dusty_wind_full": ("PBC_model/", "dusty_wind.par", "silicate.spc", [300], "dusty_wind", "noinit"),
 }
 
 KEEP_FINAL = ("dt_sequence", "t_max", "t_max_deck", "steps", "globalTime", "dt", "cflfactor", "timestep_rad2", "cfl_step",
@@ -82,7 +85,7 @@ def run_case(name):
         keep = {key: v for key, v in fin.items()
                 if key in KEEP_FINAL or (key[0] == "s" and "." in key and key.split(".", 1)[1] in KEEP_SPECIES)}
         write_dump(os.path.join(HERE, f"{name}_k{k}.bin"), keep)
-        if k == steps[0]:
+        if k == steps[0] and "noinit" not in CASES[name]:
             init = read_dump(out + "_init.bin")
             write_dump(os.path.join(HERE, f"{name}_init.bin"), init)
         print(f"{name}: k={k} t={fin['globalTime'][0]:.6e} dt={fin['dt'][0]:.6e}")

@@ -159,11 +159,24 @@ def plugin_lib():
     return path
 
 
-def _dusty_wind(plugin_lib, monkeypatch, ncols=1, overrides=None):
+def _dusty_wind(plugin_lib, monkeypatch, ncols=1, overrides=None, par="dusty_wind_1k.par"):
     from conftest import ROOT
     monkeypatch.chdir(os.path.join(ROOT, "oracle", "decks"))                  # inputdata/smalldust.opa, relative to the CWD
-    return A.Ensemble.from_files(os.path.join(GOLDEN, "decks") + "/", "dusty_wind_1k.par", "silicate.spc", ncols=ncols,
+    return A.Ensemble.from_files(os.path.join(GOLDEN, "decks") + "/", par, "silicate.spc", ncols=ncols,
                                  overrides=overrides, lib=plugin_lib)
+
+
+def test_plugin_shipped_deck_unmodified(plugin_lib, monkeypatch):
+    """PBC_model/dusty_wind.par exactly as shipped: 4002 cells (a long column: 512 threads, work arrays in HBM) + the plugin."""
+    from aiodump import read_dump
+    ens = _dusty_wind(plugin_lib, monkeypatch, par="dusty_wind.par")
+    assert ens.num_cells == 4002
+    ref = read_dump(os.path.join(GOLDEN, "p2_dusty_wind_full_k300.bin"))
+    ens.advance(300)
+    st = ens.status(0)
+    assert st["steps"] == 300 and st["state"] == 0 and abs(st["t"] - ref["globalTime"][0]) <= 1e-9 * ref["globalTime"][0]
+    errs = compare_with_golden(ens, ref)
+    assert max(errs.values()) < 1e-8, errs
 
 
 @pytest.mark.parametrize("k,tol", [(1, 1e-10), (100, 1e-8), (1000, 1e-8)])
