@@ -100,9 +100,8 @@ static void check_supported(const Problem& q) {
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && q.num_species > 8) fail("simple FLD + collisional heating with more than 8 species");
     if (q.use_rad_fluxes == 2 && q.num_species > 1 && q.use_collisional_heating && !q.update_coll_frequently) fail("UPDATE_COLL_FREQUENTLY 0");
     if (q.use_rad_fluxes && std::string("CPTKD").find(q.opacity_model) == std::string::npos) fail(std::string("opacity model ") + q.opacity_model);
-    // the analytic 2/3-species drag solver is not built; with hydro off for the whole run the reference never calls it
-    // (advection.cpp:208-212: compute_drag_update only if do_hydrodynamics or friction_solver > 0)
-    if (q.num_species > 1 && q.friction_solver == 0 && (q.do_hydrodynamics || q.start_hydro_time > 0)) fail("FRICTION_SOLVER 0 (analytic) with >1 species");
+    // with hydro off the reference calls compute_drag_update only for friction_solver > 0 (advection.cpp:208-212)
+    if (q.num_species > 1 && q.friction_solver == 0 && !q.do_hydrodynamics && q.start_hydro_time > 0) fail("FRICTION_SOLVER 0 together with START_HYDRO_TIME");
     if (q.init_J_factor > 1e10) fail("INIT_J_FACTOR > 1e10");
     for (auto& sp : q.species) {
         if ((sp.boundary_left == 0 || sp.boundary_right == 0) && !hooks_compiled())
@@ -139,8 +138,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.collision_model = q0.collision_model; p.opacity_model = q0.opacity_model;
     p.use_avg_temperature = q0.use_avg_temperature; p.update_coll_frequently = q0.update_coll_frequently;
     p.avg_temperature_t0 = q0.avg_temperature_t0; p.avg_temperature_t1 = q0.avg_temperature_t1;
-    im->has_friction = (q0.friction_solver > 0 && S > 1);      // compute_drag_update, source.cpp:233-243 (solver 0 is rejected above
-                                                               // unless hydro stays off, in which case nothing is called)
+    // compute_drag_update (source.cpp:233-243): numeric solver whenever S > 1; the analytic one (0) only while hydro is on
+    im->has_friction = S > 1 && (q0.friction_solver > 0 || (q0.friction_solver == 0 && q0.do_hydrodynamics));
     p.last_kernel = q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
     p.max_timestep_change = q0.max_timestep_change; p.dt_min_init = q0.dt_min_init; p.dt_max = q0.dt_max;
     p.energy_epsilon = q0.energy_epsilon; p.CFL_break_time = q0.CFL_break_time;

@@ -115,6 +115,78 @@ __device__ __forceinline__ double alpha_pair(const DevParams& p, int si, int sj,
     return alpha_local;
 }
 
+// Friction solver 0 (source.cpp:249-420): closed-form implicit drag for two species, the reference's (self-declared
+// experimental) determinant formula for three, nothing for more.  Restated expression by expression, including the dust
+// branch's `species[0].is_dust_like` tested twice (source.cpp:283-286) and the `a(0,1)* + a(0,2)` of its v2a line (:377).
+template <int SS>
+__device__ __forceinline__ void friction_analytic(const DevParams& p, const int S, const double dt, const double* rho, const double* v,
+                                                  const double* T, const double* nd, double* x, double* heat) {
+    if (S == 2 && SS >= 2) {
+        const SpeciesConst s0 = p.sp[0], s1c = p.sp[1];
+        const double v1b = v[0], v2b = v[1];
+        double alpha;
+        if (p.collision_model == 'C') alpha = p.alpha_collision;
+        else {
+            const double m0 = s0.mass_amu * C_AMU, m1 = s1c.mass_amu * C_AMU;
+            const double mumass = m0 * m1 / (m0 + m1);
+            const double meanT = (m1 * T[0] + m0 * T[1]) / (m0 + m1);
+            if (s0.is_dust_like || s1c.is_dust_like) {
+                const double RHO_DUST = 1;
+                double r0 = 0, r1 = 0;
+                if (s0.is_dust_like) r0 = pow(3 * m0 / (4 * M_PI * RHO_DUST), 1 / 3.);
+                if (s0.is_dust_like) r1 = pow(3 * m1 / (4 * M_PI * RHO_DUST), 1 / 3.);
+                const double A = M_PI * (r0 + r1) * (r0 + r1);
+                const double v_th = sqrt(8 * C_KB * meanT / (M_PI * mumass));
+                alpha = 4 / 3. * rho[1] * v_th * A / (m0 + m1);
+            } else {
+                const double coll_b = 5.0e17 * pow(meanT, 0.75);
+                alpha = C_KB * meanT * nd[1] / (m0 * coll_b);
+                alpha *= p.alpha_collision;
+            }
+        }
+        const double eps = rho[0] / rho[1];
+        const double f1 = (1. + dt * alpha) / (1. + dt * alpha * (1. + eps));
+        const double f2 = dt * alpha * eps / (1. + dt * alpha);
+        const double v2a = (v2b + v1b * f2) * f1;
+        const double v1a = v1b - (v2a - v2b) / eps;
+        x[0] = v1a; x[1] = v2a;
+        const double v_half = 0.5 * (v1a + v1b) - 0.5 * (v2a + v2b);
+        const double v_end = v1a - v2a;
+        heat[0] = dt * alpha * (s1c.mass_amu / (s0.mass_amu + s1c.mass_amu)) * v_half * v_end;
+        heat[1] = dt * alpha * eps * (s0.mass_amu / (s0.mass_amu + s1c.mass_amu)) * v_half * v_end;
+    } else if (S == 3 && SS >= 3) {
+        double a[3][3];
+        for (int si = 0; si < 3; si++)
+            for (int sj = 0; sj < 3; sj++) {
+                if (si == sj) a[si][sj] = 0.;
+                else if (si > sj) a[si][sj] = p.fric_mask[si * 3 + sj] * p.alpha_collision;
+                else a[si][sj] = p.fric_mask[si * 3 + sj] * p.alpha_collision * rho[sj] / rho[si];
+            }
+        const double v1b = v[0], v2b = v[1], v3b = v[2];
+        double det = -(a[0][2] + dt * a[0][2] * a[1][0] + a[0][1] * a[1][2] + dt * a[0][2] * a[1][2]) * a[2][0];
+        det += (-a[0][2] * a[1][0] - a[1][2] - dt * a[0][1] * a[1][2] - dt * a[0][2] * a[1][2]) * a[2][1];
+        det += (-a[0][1] * a[1][0] + (1. + dt * (a[0][1] + a[0][2])) * (1. + dt * (a[1][0] + a[1][2]))) * (1. + dt * (a[2][0] + a[2][1]));
+        double v1a = v1b * (-a[1][2] * a[2][1] + (1. + dt * (a[1][0] + a[1][2])) * (1. + dt * (a[2][0] + a[2][1])));
+        v1a += v2b * (a[0][1] + dt * a[0][1] * a[2][0] + dt * a[0][1] * a[2][1] + a[0][2] * a[2][1]);
+        v1a += v3b * (a[0][2] + dt * a[0][2] * a[1][0] + a[0][1] * a[1][2] + dt * a[0][2] * a[1][2]);
+        double v2a = v1b * (a[1][0] + dt * a[1][0] * a[2][0] + a[1][2] * a[2][0] + dt * a[1][0] * a[2][1]);
+        v2a += v2b * (-a[0][2] * a[2][0] + (1. + dt * (a[0][1] * +a[0][2])) * (1. + dt * (a[2][0] + a[2][1])));
+        v2a += v3b * (a[0][2] * a[1][0] + a[1][2] + dt * a[0][1] * a[1][2] + dt * a[0][2] * a[1][2]);
+        double v3a = v1b * (a[2][0] + dt * a[1][0] * a[2][0] + dt * a[1][2] * a[2][0] + a[1][0] * a[2][1]);
+        v3a += v2b * (a[0][1] * a[2][0] + a[2][1] + dt * a[0][1] * a[2][1] + dt * a[0][2] * a[2][1]);
+        v3a += v3b * (-a[0][1] * a[1][0] + (1. + dt * (a[0][1] + a[0][2])) * (1. + dt * (a[1][0] + a[1][2])));
+        v1a /= det; v2a /= det; v3a /= det;
+        x[0] = v1a; x[1] = v2a; x[2] = v3a;
+        const double m0 = p.sp[0].mass_amu, m1 = p.sp[1].mass_amu, m2 = p.sp[2].mass_amu;
+        const double d12 = (v1a - v2a) * (v1a - v2a), d13 = (v1a - v3a) * (v1a - v3a), d23 = (v2a - v3a) * (v2a - v3a);
+        double h0 = 0, h1 = 0, h2 = 0;
+        h0 += dt * a[0][1] * (m1 / (m0 + m1)) * d12; h0 += dt * a[0][2] * (m2 / (m0 + m2)) * d13;
+        h1 += dt * a[1][0] * (m0 / (m1 + m0)) * d12; h1 += dt * a[1][2] * (m2 / (m1 + m2)) * d23;
+        h2 += dt * a[2][0] * (m0 / (m2 + m0)) * d13; h2 += dt * a[2][1] * (m1 / (m2 + m1)) * d23;
+        heat[0] = h0; heat[1] = h1; heat[2] = h2;
+    }
+}
+
 template <int SS>
 __device__ __forceinline__ void friction_phase(const DevParams& p, const int col, const double dt, const double tnow, TailAcc& acc) {
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -135,7 +207,13 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
                 T[s] = e[s] / sc.cv;
             }
         }
-        double A[SS][SS], M[SS][SS], x[SS];
+        double x[SS], heat[SS];
+#pragma unroll
+        for (int si = 0; si < SS; si++) { x[si] = (si < S) ? v[si] : 0.; heat[si] = 0.; }
+        if (p.friction_solver == 0) {
+            friction_analytic<SS>(p, S, dt, rho, v, T, nd, x, heat);
+        } else {
+        double A[SS][SS], M[SS][SS];
 #pragma unroll
         for (int si = 0; si < SS; si++) {
 #pragma unroll
@@ -155,13 +233,11 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
                 else M[si][sj] = (si == sj) ? 1. : 0.;
             }
             M[si][si] = d_add(M[si][si], d_mul(dt, rowsum));
-            x[si] = (si < S) ? v[si] : 0.;
         }
         lu_solve<SS>(M, x, S);
 #pragma unroll
         for (int si = 0; si < SS; si++) {
             if (si < S) {
-                const SpeciesConst sc = p.sp[si];
                 double temp = 0;
 #pragma unroll
                 for (int sj = 0; sj < SS; sj++) {
@@ -169,9 +245,18 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
                         const double v_end = x[si] - x[sj];
                         const double v_half = 0.5 * (v_end + v[si] - v[sj]);
                         const double mj = p.sp[sj].mass_amu;
-                        temp += dt * A[si][sj] * (mj / (mj + sc.mass_amu)) * v_half * v_end;
+                        temp += dt * A[si][sj] * (mj / (mj + p.sp[si].mass_amu)) * v_half * v_end;
                     }
                 }
+                heat[si] = temp;
+            }
+        }
+        }
+#pragma unroll
+        for (int si = 0; si < SS; si++) {
+            if (si < S) {
+                const SpeciesConst sc = p.sp[si];
+                const double temp = heat[si];
                 const double en = e[si] + temp;
                 Prim3 q; q.rho = rho[si]; q.v = x[si]; q.p = en * rho[si] * sc.gm1;      // update_p_from_eint
                 double n1, n2, n3;

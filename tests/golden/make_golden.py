@@ -42,6 +42,12 @@ CASES = {
     "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", None, [1, 100, 1000]),
     # configs[3]: hydro + 2-band irradiation + simple FLD
     "c4_dynamic3_euv": ("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", None, [1, 100, 1000, 3000]),
+    # FRICTION_SOLVER 0, the closed-form two-species drag (source.cpp:249-330): constant and physical collision models
+    "f1_friction_2spc_an": ("test_files/", "friction_2spc_an.par", "friction_2spc.spc", [1, 100, 500]),
+    "f2_friction_2spc_phys_an": ("test_files/", "friction_2spc_phys_an.par", "friction_2spc.spc", [1, 100, 500]),
+    # the three-species determinant formula of the same solver (source.cpp:332-400) on the well-conditioned friction deck
+    # (our variant: friction_6spc_mild.par with 3 species and FRICTION_SOLVER 0)
+    "f3_friction_3spc_an_mild": ("test_files/", "friction_3spc_an_mild.par", "friction_6spc.spc", [100, 1000]),
     # DO_HYDRO 0: radiation-only relaxation (no hydro stages; at order 2 only the boundary conditions are applied,
     # advection.cpp:196-200; dt from the energy limiter, helpers.cpp:80-85), full FLD
     "n1_searth_nohydro": ("test2/", "SEarth_nohydro_1s1b.par", "mix_HHe.spc", [1, 100, 300]),
