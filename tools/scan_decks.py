@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--lib", default=os.path.join(ROOT, "tests", "emu", "_build", "libaiolos_emu.so"))
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
+    if a.out:
+        a.out = os.path.abspath(a.out)
     subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), a.rundir], check=True, stdout=subprocess.DEVNULL)
     os.chdir(a.rundir)
     rows = []
