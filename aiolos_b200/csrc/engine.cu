@@ -621,28 +621,40 @@ void Engine::upload_u(const double* src) {
 }
 // Asynchronous variant for pipelined callers: the copy runs on a second stream into a staging buffer while the compute stream
 // is still stepping; commit_upload() makes the staged state the current one (pointer swap, ordered by events).
+// Pipelined upload.  The host buffer is unpadded ([3][ncol][S][N+2]); a pitched 2-D copy of 12 288 rows of 7 992 bytes runs
+// at ~80 % of the PCIe rate, so the copy stream moves the buffer as ONE contiguous transfer into a raw staging area and the
+// re-pitching into the padded device layout is a device kernel on the compute stream at commit time (98 MB at HBM speed).
+struct RepitchArgs { const double* src; double* dst; int N2, NP; };
+__global__ void k_repitch(RepitchArgs a) {
+    const size_t row = blockIdx.x;
+    const double* s = a.src + row * a.N2;
+    double* d = a.dst + row * a.NP;
+    for (int j = threadIdx.x; j < a.N2; j += blockDim.x) d[j] = s[j];
+}
 void Engine::upload_u_async(const double* src) {
     DevParams& p = im->p;
     const size_t rows = (size_t)3 * p.ncol * p.S;
     if (!im->copy_stream) {
         CK(cudaStreamCreateWithFlags(&im->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&im->ev_up)); CK(cudaEventCreate(&im->ev_free));
-        im->u_stage = im->dalloc<double>(rows * p.NP);
+        im->u_stage = im->dalloc<double>(rows * p.N2);
         CK(cudaStreamSynchronize(im->stream));
         CK(cudaEventRecord(im->ev_free, im->stream));
     }
-    CK(cudaStreamWaitEvent(im->copy_stream, im->ev_free, 0));      // the staging buffer was the live state until the last swap
-    CK(cudaMemcpy2DAsync(im->u_stage, (size_t)p.NP * sizeof(double), src, (size_t)p.N2 * sizeof(double), (size_t)p.N2 * sizeof(double), rows,
-                         cudaMemcpyHostToDevice, im->copy_stream));
+    CK(cudaStreamWaitEvent(im->copy_stream, im->ev_free, 0));      // the previous commit has finished reading the staging area
+    CK(cudaMemcpyAsync(im->u_stage, src, rows * p.N2 * sizeof(double), cudaMemcpyHostToDevice, im->copy_stream));
     CK(cudaEventRecord(im->ev_up, im->copy_stream));
     im->staged = true;
 }
 void Engine::commit_upload() {
     if (!im->staged) throw std::invalid_argument("commit_upload without a pending upload_u_async");
     DevParams& p = im->p;
+    const size_t rows = (size_t)3 * p.ncol * p.S;
     CK(cudaStreamWaitEvent(im->stream, im->ev_up, 0));
-    std::swap(p.u, im->u_stage);
-    CK(cudaEventRecord(im->ev_free, im->stream));                  // kernels launched before this point may still read the old buffer
+    RepitchArgs a{im->u_stage, p.u, p.N2, p.NP};
+    AIO_LAUNCH(k_repitch, (unsigned)rows, 256, 0, im->stream, a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(im->ev_free, im->stream));
     im->staged = false;
 }
 void Engine::download_u(double* dst) {
