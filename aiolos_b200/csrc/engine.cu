@@ -93,7 +93,7 @@ static void check_supported(const Problem& q) {
     if (q.use_drag_predictor_step) fail("PARI_SECONDORDER_DRAG 1");
     if (q.use_total_pressure) fail("USE_TOTAL_PRESSURE 1");
     if (q.use_convective_fluxes) fail("USE_CONVECTION 1");
-    if (q.use_planetary_temperature) fail("USE_PLANET_TEMPERATURE 1");
+    if (q.use_planetary_temperature && q.use_rad_fluxes == 1 && q.num_bands_in < q.num_bands_out) fail("USE_PLANET_TEMPERATURE 1 with fewer incoming than outgoing bands");
     if (q.radiation_matter_equilibrium_test != 0) fail("RAD_MATTER_EQUI_TEST != 0");
     if (q.use_rad_fluxes < 0 || q.use_rad_fluxes > 2) fail("PARI_USE_RADIATION outside 0..2");
     if (q.use_rad_fluxes == 2 && q.num_bands_out != 1) fail("simple FLD solver needs NUM_BANDS_OUT 1");

@@ -56,7 +56,7 @@ __host__ __device__ inline FullDims full_dims(int Bout, int S, int Bin) {
     d.LD = d.n + Bout + 1; if ((d.LD & 1) == 0) d.LD++;      // augmented row: S | u columns | rhs ; odd => conflict-free
     d.LDX = Bout + 1; if ((d.LDX & 1) == 0) d.LDX++;
     // tile, previous X (+A), x of the cell above, fac[S][Bout], contributions[S][Bin], scratch
-    d.per_warp = d.n * d.LD + d.n * d.LDX + d.n + S * Bout + S * Bin + 2 * S + 8;
+    d.per_warp = d.n * d.LD + d.n * d.LDX + d.n + S * Bout + S * Bin + 2 * S + 8 + Bout + Bin;
     return d;
 }
 
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
     double* facs = xs + n;                           // [S][Bout]
     double* contrib = facs + S * Bout;               // [S][Bin]
     double* misc = contrib + S * Bin;                // [2S + 8]
+    double* dcore = misc + 2 * S + 8;                // [Bout] D_core of the surface cell (USE_PLANET_TEMPERATURE, radiation.cpp:464)
+    double* ssurf = dcore + Bout;                    // [Bin]  S_band(num_ghosts-1, b): stellar flux reaching the surface
     const int KA = Bin + 2 * Bout;
     const double* kap = p.kappa_avg;
     double* Xg = p.Xstore + (size_t)col * N2 * n * (Bout + 1);
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
                 double dSb;
                 if (j < N + 1) {
                     const double Sb = F * exp(-rad_above);
+                    if (j == p.ng - 1) ssurf[b] = Sb;
                     dSb = 0.25 * Sb / dxj * (1. - p.bond_albedo);
                     const double dtau_tot = -(rad_above - rad_j);
                     double dS_he = dSb;
@@ -195,6 +198,21 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
             }
             D_prev = D_i;
             if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
+            if (i == p.ng - 1 && p.use_planetary_temperature) {      // surface cell radiates at T_planet (radiation.cpp:451-472)
+                const double Tp = cst.T_planet;
+                double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp));
+                if (Tp < 0) Ssrc *= -1;
+                const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+                double rhokr = smax(2. * (to_i * to_ip) / (to_i + to_ip), 4. / 3. / dxc);
+                rhokr = smin(0.5 * (to_i + to_ip), rhokr);
+                const double tau_inv = 1 / (dxc * rhokr);
+                const double R = p.xi_rad * tau_inv * fabs(Jnext - Jcur) / (Jnext + 1e-300);
+                const double Dc = flux_limiter(R) * tau_inv;
+                dcore[b] = Dc;
+                const double Chi = 0.25;
+                const double sj = __ldg(p.surf + i);
+                l_rr = 0; d = 0.5 * (Dc + Chi) * sj; u_rr = -0.5 * (Dc - Chi) * sj; rhs = sj * Ssrc / (4 * C_PI);
+            }
             if (p.closed_radiative_boundaries) {
                 if (i >= N2 - p.ng) { l_rr = -d; u_rr = 0; rhs = 0; }
             } else if (i == N + 1) {
@@ -398,6 +416,7 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
     // ---- back sweep  x_i = A_i - X_i x_{i+1},  store J, clamp T, e <- T, p <- e, cons <- prim, step tail ---------------------------
     TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
     int negJ = 0; double negJval = 0;
+    double Jtop = 0;                    // Jrad_FLD(num_cells, b) of this lane's band (advection.cpp:320-322)
     for (int i = N2 - 1; i >= 0; i--) {
         const double* Xi = Xg + (size_t)i * n * (Bout + 1);
         double x = 0;
@@ -416,8 +435,9 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
             double Jv = x;
             if (p.couple_J_into_T && i <= N - 1 && Jv < 0) {           // advection.cpp:308-338
                 if (Jv > -1e-10) Jv *= -1.;
-                else { negJ = 1; negJval = Jv; }
+                else if (!(i < N && p.use_planetary_temperature && Jtop > 0)) { negJ = 1; negJval = Jv; }
             }
+            if (i == N) Jtop = Jv;
             p.J[idx_J(p, col, lane, i)] = Jv;
         } else if (isT) {
             const int s = sT;
@@ -436,6 +456,20 @@ __global__ void __launch_bounds__(64, (NB > 0) ? 1 : 8) k_rad_full(DevParams p) 
             p.u[idx_u(p, 0, col, s, i)] = n1; p.u[idx_u(p, 1, col, s, i)] = n2; p.u[idx_u(p, 2, col, s, i)] = n3;
             tail_cell(p, col, s, i, q.v, cs_old, e, T, acc);
         }
+    }
+    // slab model of the planet's surface temperature (radiation.cpp:812-828), bands summed in order by one lane
+    __syncwarp();
+    if (p.use_planetary_temperature && lane == 0) {
+        double F = 0, S_surf = 0;
+        for (int b = 0; b < Bout; b++) {
+            F -= 4 * C_PI * dcore[b] * (p.J[idx_J(p, col, b, p.ng)] - p.J[idx_J(p, col, b, p.ng - 1)]);
+            S_surf += 0.25 * ssurf[b];
+        }
+        const double S_tot = S_surf - F + C_SIGMA_RAD * (p.T_int * p.T_int) * (p.T_int * p.T_int);
+        double Tp = cst.T_planet;
+        if (p.core_cv > 0) { const double denom = 4 * C_SIGMA_RAD * Tp * Tp * Tp + p.core_cv / dt; Tp += S_tot / denom; }
+        else Tp = pow(pow(Tp, 4) + S_tot / C_SIGMA_RAD, 0.25);
+        cst.T_planet = Tp;
     }
     const double ms = warp_max(acc.minstep), md = warp_max(acc.maxde);
     const int bad = warp_or(acc.bad), nj = warp_or(negJ);
