@@ -6,7 +6,7 @@
 set -e
 RUN="$1"; REF="${2:-/root/reference}"
 mkdir -p "$RUN"
-for d in runs_mdot_vs_euv_plot runs_searth test_files test2 c2ray runs_earth PBC_model; do
+for d in runs_mdot_vs_euv_plot runs_searth test_files test2 c2ray runs_earth PBC_model runs_convect runs_hjescape runs_schulik2020 friction_debug; do
     [ -d "$REF/$d" ] && { rm -rf "$RUN/$d"; cp -r "$REF/$d" "$RUN/$d"; }
 done
 cp "$REF/test_files/irradiation.spc" "$RUN/test2/"   # SEarth_opacities_1s22b.par names no species file
