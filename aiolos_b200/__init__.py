@@ -35,6 +35,10 @@ class AiolosError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"aiolos_b200 error {code}: {msg}")
         self.code = code
+        self.msg = msg
+
+    def __reduce__(self):           # picklable (multiprocessing workers)
+        return (AiolosError, (self.code, self.msg))
 
 
 class _Override(C.Structure):

@@ -76,6 +76,8 @@ struct DevParams {
     int closed_radiative_boundaries, use_planetary_temperature, couple_J_into_T, solve_for_j;
     int radiation_matter_equilibrium_test, use_total_pressure, collision_model, opacity_model;
     int use_avg_temperature, update_coll_frequently;
+    int use_self_gravity, use_linear_gravity, use_tides;   // update_mass_and_pot() per step (source.cpp:50-109) when self-gravity is on
+    double planet_position, rs;
     int do_hydrodynamics;       // DO_HYDRO; 0 = no hydro stages until t > start_hydro_time (advection.cpp:62-64,139,170-200)
     double start_hydro_time;
     double avg_temperature_t0, avg_temperature_t1;
@@ -143,7 +145,7 @@ __host__ __device__ inline size_t idx_J(const DevParams& p, int col, int b, int 
 // the previous step (reflecting / periodic / user hook: phi[ghost] = phi[active]) is undone before phi_s is refreshed, while
 // the outermost entry num_cells+1 and the entries 0, 1 keep the boundary condition's value.
 __device__ __forceinline__ double phi_snapshot(const DevParams& p, int col, const double* phi, int j) {
-    return (j == p.N) ? p.phiN[col] : phi[j];
+    return (j == p.N && !p.use_self_gravity) ? p.phiN[col] : phi[j];     // with self-gravity phi[2..N] is recomputed in the kernel
 }
 
 // Is the hydrodynamics module on for the step that starts at time t?  (advection.cpp:62-64: the switch flips, for good, once
@@ -154,6 +156,7 @@ __device__ __forceinline__ bool hydro_on(const DevParams& p, double t) {
 
 // physical constants, verbatim values of aiolos.h:47-77
 constexpr double C_G = 6.678e-8, C_PI = 3.141592653589793, C_CLIGHT = 2.99792458e10, C_AMU = 1.66054e-24;
+constexpr double C_AU = 1.495978707e13;
 constexpr double C_KB = 1.380649e-16, C_SIGMA_RAD = 5.670374419e-5, C_ELM_CHARGE = 4.80320425e-10;
 constexpr double C_K_TO_EV = 8.621738e-5, C_EV_TO_K = 1. / C_K_TO_EV;
 

@@ -86,7 +86,7 @@ static void check_supported(const Problem& q) {
     if (q.num_species < 1 || q.num_species > MAXS) fail("num_species outside 1.." + std::to_string(MAXS));
     if (q.num_bands_in > MAXB || q.num_bands_out > MAXB) fail("more than 32 radiation bands");
     if (q.num_cells < 6) fail("fewer than 6 cells");
-    if (q.use_self_gravity) fail("PARI_SELF_GRAV_SWITCH 1");
+    if (q.use_self_gravity && q.num_species > 1) fail("PARI_SELF_GRAV_SWITCH 1 with several species");
     if (q.rs_time > 0) fail("PARI_SMOOTHING_TIME > 0 (time-dependent potential)");
     if (q.K_zz_init != 0) fail("KZZ_INIT != 0");
     if (q.photochemistry_level != 0) fail("PHOTOCHEM_LEVEL != 0 (SURVEY 8 f1: next)");
@@ -131,6 +131,8 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.order = q0.order; p.geometry = q0.geometry; p.problem_number = q0.problem_number;
     p.use_rad_fluxes = q0.use_rad_fluxes; p.friction_solver = q0.friction_solver;
     p.do_hydrodynamics = q0.do_hydrodynamics; p.start_hydro_time = q0.start_hydro_time;
+    p.use_self_gravity = q0.use_self_gravity; p.use_linear_gravity = q0.use_linear_gravity; p.use_tides = q0.use_tides;
+    p.planet_position = q0.planet_position; p.rs = q0.rs;
     p.use_collisional_heating = q0.use_collisional_heating; p.photochemistry_level = q0.photochemistry_level;
     p.closed_radiative_boundaries = q0.closed_radiative_boundaries; p.use_planetary_temperature = q0.use_planetary_temperature;
     p.couple_J_into_T = q0.couple_J_into_T; p.solve_for_j = q0.solve_for_j;
@@ -307,7 +309,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
     for (auto& sp : q0.species) if (sp.boundary_left == 0 || sp.boundary_right == 0) im->fused = false;   // hooks flag errors through p.cs
     im->hydro_switch = (!q0.do_hydrodynamics || q0.start_hydro_time > 0);
-    if (im->hydro_switch) { im->v2 = false; im->fused = false; }   // DO_HYDRO 0 / START_HYDRO_TIME: only the v1 kernels carry the switch
+    if (im->hydro_switch || q0.use_self_gravity) { im->v2 = false; im->fused = false; }   // DO_HYDRO 0 / START_HYDRO_TIME: only the v1 kernels carry the switch
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     // work arrays that do not fit in one CTA's shared memory (long columns, or many species in the simple FLD kernel) go to HBM
     p.scratch = nullptr; p.scratch_stride = 0; p.scratch_hydro = p.scratch_rad = 0;
@@ -551,7 +553,7 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");
     } else if (key == "kernels") {
         if (value == "v1") im->v2 = false;
-        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME run the v1 kernels"); im->v2 = true; }
+        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch || im->p.use_self_gravity) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity run the v1 kernels"); im->v2 = true; }
         else throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
         if (total_steps() != 0) throw std::invalid_argument("option kernels must be set before the first step");
     } else throw std::invalid_argument("unknown option '" + key + "'");

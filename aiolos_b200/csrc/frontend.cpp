@@ -812,7 +812,29 @@ bool problem_from_files(const std::string& dir, const std::string& par_solo, con
         const int NS = q.num_species;
         S.sp.resize(NS);
         for (int s = 0; s < NS; s++) construct_species(S, s, par, speciesfile);
-        if (q.use_self_gravity) throw std::runtime_error("unsupported configuration: PARI_SELF_GRAV_SWITCH 1");
+        if (q.use_self_gravity) {                              // init_and_bounds.cpp:645-662: relax the atmosphere in its own potential
+            std::vector<double> enclosed(N2, 0.);
+            for (int cnt = 0; cnt < 50; cnt++) {
+                enclosed[0] = q.planet_mass; enclosed[1] = q.planet_mass;       // update_mass_and_pot(), source.cpp:50-109, at globalTime 0
+                for (int i = 2; i <= N; i++) {
+                    double dens = 0.;
+                    for (auto& sp : S.sp) dens += sp.d.u1[i];
+                    double xn3 = q.x_i[i]; xn3 = xn3 * xn3 * xn3;
+                    double xl3 = q.x_i[i - 1]; xl3 = xl3 * xl3 * xl3;
+                    enclosed[i] = enclosed[i - 1] + 4. * 3.141592 * (xn3 - xl3) / 3. * dens;
+                    q.phi[i] = S.get_phi_grav(q.x_i12[i], enclosed[i]);
+                    if (q.use_tides == 1) {
+                        double d3 = q.planet_semimajor * au;
+                        d3 = d3 * d3 * d3;
+                        q.phi[i] -= 0.5 * 3. * G * q.star_mass * q.x_i12[i] * q.x_i12[i] / d3;
+                    }
+                }
+                for (int s = 0; s < NS; s++) {
+                    for (int i = 0; i < N2; i++) S.sp[s].phi_s[i] = q.phi[i];
+                    initialize_hydrostatic_atmosphere(S, S.sp[s], s, par);
+                }
+            }
+        }
         q.friction_coeff_mask.assign((size_t)NS * NS, 1.); q.inv_totmasses.assign((size_t)NS * NS, 0.); q.resonant_pair_matrix.assign((size_t)NS * NS, 1.);
         for (int si = 0; si < NS; si++)
             for (int sj = 0; sj < NS; sj++) {

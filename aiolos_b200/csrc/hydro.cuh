@@ -291,6 +291,40 @@ __device__ inline void tail_commit(const DevParams& p, int col, TailAcc a, doubl
     tail_commit_on(p.cs[col], a, red, negJ, Jval);
 }
 
+// update_mass_and_pot() with PARI_SELF_GRAV_SWITCH 1 (source.cpp:50-109): enclosed mass by the reference's sequential sum (one
+// lane, so that the rounding sequence is the reference's), then phi[2..N] = get_phi_grav(x_i12, M_enc) (+ tides).  RHO holds the
+// summed species density per cell; W and EM are work arrays of N+2 doubles.
+__device__ inline void self_gravity_update(const DevParams& p, const int col, double* W, const double* RHO, double* EM) {
+    const int tid = threadIdx.x, NT = blockDim.x, N = p.N;
+    for (int j = tid + 2; j <= N; j += NT) {
+        double xn3 = p.x_i[j]; xn3 = xn3 * xn3 * xn3;
+        double xl3 = p.x_i[j - 1]; xl3 = xl3 * xl3 * xl3;
+        W[j] = 4. * 3.141592 * (xn3 - xl3) / 3.;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double em = p.planet_mass;
+        EM[0] = em; EM[1] = em;
+        for (int j = 2; j <= N; j++) { em = em + W[j] * RHO[j]; EM[j] = em; }
+    }
+    __syncthreads();
+    double* phi = p.phi + idx_c(p, col, 0);
+    for (int j = tid + 2; j <= N; j += NT) {
+        const double r = p.x_i12[j], mass = EM[j];
+        double ph;
+        if (p.use_linear_gravity) ph = -C_G * mass * fabs(p.domain_max - r);
+        else if (fabs(r - p.planet_position) > p.rs) ph = -C_G * mass / fabs(r - p.planet_position);
+        else ph = -C_G * mass * (pow(r - p.planet_position, 3.) / pow(p.rs, 4.) - 2. * pow(r - p.planet_position, 2.) / pow(p.rs, 3.) + 2. / p.rs);
+        if (p.use_tides == 1) {
+            double d3 = p.planet_semimajor * C_AU;
+            d3 = d3 * d3 * d3;
+            ph -= 0.5 * 3. * C_G * p.star_mass * r * r / d3;
+        }
+        phi[j] = ph;
+    }
+    __syncthreads();
+}
+
 // One column, one time step of hydrodynamics for all species.  `sm` = dynamic shared memory of the CTA
 // (9*N2 + 32 + 12*ng doubles).  `snap` != 0 refreshes the phi_s snapshot first.
 template <int CPT>
@@ -308,7 +342,12 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
 
     // phi_s snapshot for all species before any BC edits phi (update_kzz_and_gravpot, advection.cpp:101-102 /
     // source.cpp:207-209 with K_zzf = 1).  phi is static after the first step (engine.cu), so steps >= 2 skip it.
-    if (snap) {
+    if (p.use_self_gravity) {           // advection.cpp:99 (single species: checked at create time)
+        for (int j = tid; j < N2; j += NT) Pv[j] = p.u[idx_u(p, 0, col, 0, j)];
+        __syncthreads();
+        self_gravity_update(p, col, Pr, Pv, Pp);
+    }
+    if (snap || p.use_self_gravity) {
         const double* phi = p.phi + idx_c(p, col, 0);
         for (int s = 0; s < p.S; s++) {
             double* phis = p.phis + idx_s(p, col, s, 0);
@@ -443,6 +482,13 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
                 } else {
                     u1[k] += (t1 - d1[k]) * dt / 2; u2[k] += (t2 - d2[k]) * dt / 2; u3[k] += (t3 - d3[k]) * dt / 2;
                 }
+            }
+            if (p.use_self_gravity && stage == 0 && nstage == 2) {      // second update_mass_and_pot() at t + dt (advection.cpp:168-169):
+                __syncthreads();                                         // changes base->phi (the stage-2 boundary conditions read it), not phi_s
+#pragma unroll
+                for (int k = 0; k < CPT; k++) { const int j = tid + k * NT; if (j < N2) Pv[j] = u1[k]; }
+                __syncthreads();
+                self_gravity_update(p, col, Pr, Pv, Pp);
             }
         }
         // ---- write back; final compute_pressure (advection.cpp:204-205) and tail -----------------------------

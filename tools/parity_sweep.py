@@ -22,6 +22,13 @@ ORACLE = os.path.join(ROOT, "oracle", "_ref", "aiolos_ref_dump")
 
 
 def one(args):
+    try:
+        return _one(args)
+    except Exception as ex:      # noqa: BLE001  (a worker must never die: every failure is a row of the report)
+        return (args[0] + args[1], "error", str(ex).replace("\n", " ")[:160])
+
+
+def _one(args):
     d, f, k = args
     import aiolos_b200 as A
     from aiodump import read_dump
@@ -69,6 +76,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=3)
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default="")
+    ap.add_argument("--resume", default=None, help="log of an earlier run (one result tuple per line): those decks are kept, not rerun")
     a = ap.parse_args()
     out = os.path.abspath(a.out) if a.out else None
     subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), RUN], check=True, stdout=subprocess.DEVNULL)
@@ -78,11 +86,21 @@ def main():
         if os.path.isdir(os.path.join(RUN, d)) and a.only in p:
             work.append((d, os.path.basename(p), a.steps))
     rows = []
+    if a.resume and os.path.exists(a.resume):
+        import ast
+        for ln in open(a.resume):
+            if ln.startswith("('"):
+                try:
+                    rows.append(ast.literal_eval(ln.strip()))
+                except (ValueError, SyntaxError):
+                    pass
+        done = {r[0] for r in rows}
+        work = [w for w in work if w[0] + w[1] not in done]
     with ProcessPoolExecutor(a.jobs) as ex:
         for r in ex.map(one, work):
             rows.append(r)
             print(r, flush=True)
-    n = {t: sum(1 for r in rows if r[1] == t) for t in ("ok", "both-crashed", "MISMATCH", "refused", "oracle-failed", "oracle-timeout")}
+    n = {t: sum(1 for r in rows if r[1] == t) for t in ("ok", "both-crashed", "MISMATCH", "refused", "oracle-failed", "oracle-timeout", "error")}
     lines = [f"# Parity sweep over the shipped decks, {a.steps} steps each (CTA emulator vs the unmodified reference)", "",
              f"{len(rows)} decks: " + ", ".join(f"{v} {k}" for k, v in n.items() if v), "",
              "| deck | result | detail |", "|---|---|---|"]
