@@ -169,6 +169,19 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local)
+    if world > 1:
+        # one rank per GPU: keep the rank (and hence the pinned host buffers it first-touches for the end-to-end leg) on the
+        # CPU cores / NUMA node next to its GPU; without this every rank's H2D traffic may cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:      # noqa: BLE001  (affinity is an optimisation only)
+            pass
     dist = None
     if world > 1:
         import torch.distributed as dist
