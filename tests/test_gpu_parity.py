@@ -210,3 +210,20 @@ def test_plugin_dt_sequence_and_ensemble(plugin_lib, monkeypatch):
     a, b, c = (ens.get("u1", col, 1) for col in range(3))
     assert np.array_equal(a, c) and not np.array_equal(a, b)                  # columns are independent; the override took effect
     assert (ens.status_all()["state"] == 0).all()
+
+
+def test_fused_kernel_variants_agree(lib):
+    """The 2-CTA/SM (128-register) build of the fused step kernel and a different steps-per-launch are the same arithmetic:
+    bit-identical state and clocks after 100 steps."""
+    base = None
+    for opts in ({}, {"step1_ctas": "2"}, {"steps_per_launch": "7"}, {"fused": "0"}):
+        ens, ref = run_case(A, lib, "c4_dynamic3_euv", 100, ncols=4, options=opts)
+        u = ens.download_state()
+        st = ens.status_all()
+        assert (st["steps"] == 100).all()
+        if base is None:
+            base = (u, st["t"].copy())
+        elif "fused" in opts:          # the unfused v2/v3 kernels: same algorithms, separate compilation
+            assert np.allclose(u, base[0], rtol=1e-11, atol=0) and np.allclose(st["t"], base[1], rtol=1e-12)
+        else:
+            assert np.array_equal(u, base[0]) and np.array_equal(st["t"], base[1]), opts
