@@ -147,7 +147,7 @@ def main():
                                                               "1e-20 s and reaches the CFL regime after ~450 steps")
     ap.add_argument("--ref-steps", type=int, default=4000, help="time steps per column per bench step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="aio_set_option pairs (kernel variants)")
     args = ap.parse_args()
 
