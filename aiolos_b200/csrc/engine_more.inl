@@ -10,7 +10,8 @@ void Engine::launch_friction() {
     else if (p.S <= 4) AIO_LAUNCH(k_friction<4>, ncol, NT, 0, im->stream, p);
     else if (p.S <= 6) AIO_LAUNCH(k_friction<6>, ncol, NT, 0, im->stream, p);
     else if (p.S <= 8) AIO_LAUNCH(k_friction<8>, ncol, NT, 0, im->stream, p);
-    else throw std::runtime_error("unsupported configuration: more than 8 species with friction");
+    else if (p.S <= 16) AIO_LAUNCH(k_friction<16>, ncol, NT, 0, im->stream, p);
+    else throw std::runtime_error("unsupported configuration: more than 16 species with friction");
 }
 
 // Full FLD (PARI_USE_RADIATION 1): one warp per column, two columns per CTA (rad_full.cuh).

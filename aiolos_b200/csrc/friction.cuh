@@ -12,55 +12,57 @@
 namespace aio {
 
 // In-place LU with partial pivoting + solve of M x = b for one cell.  SS = compile-time capacity, S = runtime size.
+// Fully unrolled (matrix in registers) up to SS = 8; the SS = 16 instantiation keeps its loops rolled and the matrix in local
+// memory -- capacity for the rare decks with 9..16 species, not speed.
 template <int SS>
 __device__ __forceinline__ void lu_solve(double (&M)[SS][SS], double (&x)[SS], int S) {
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
     for (int k = 0; k < SS; k++) {
         if (k < S) {
             int piv = k; double big = fabs(M[k][k]);
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
             for (int r = k + 1; r < SS; r++) if (r < S) { double v = fabs(M[r][k]); if (v > big) { big = v; piv = r; } }
             if (big != 0.0) {
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                 for (int r = k + 1; r < SS; r++) {
                     if (r == piv) {
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                         for (int c = 0; c < SS; c++) { double t = M[k][c]; M[k][c] = M[r][c]; M[r][c] = t; }
                         double t = x[k]; x[k] = x[r]; x[r] = t;       // permutation applied to the rhs as it is found
                     }
                 }
                 const double d = M[k][k];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                 for (int r = k + 1; r < SS; r++) if (r < S) M[r][k] /= d;
             }
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
             for (int r = k + 1; r < SS; r++) {
                 if (r < S) {
                     const double l = M[r][k];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                     for (int c = k + 1; c < SS; c++) if (c < S) M[r][c] = d_fnma(l, M[k][c], M[r][c]);
                 }
             }
         }
     }
     // NOTE: swapping x while factoring is equivalent to applying P afterwards (row k is final once step k is done).
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
     for (int i = 0; i < SS; i++) {
         if (i < S) {
             const double xi = x[i];
             if (xi != 0.0) {
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                 for (int r = i + 1; r < SS; r++) if (r < S) x[r] = d_fnma(xi, M[r][i], x[r]);
             }
         }
     }
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
     for (int i = SS - 1; i >= 0; i--) {
         if (i < S) {
             if (x[i] != 0.0) {
                 x[i] /= M[i][i];
                 const double xi = x[i];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                 for (int r = 0; r < i; r++) x[r] = d_fnma(xi, M[r][i], x[r]);
             }
         }
@@ -194,7 +196,7 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
 
     for (int j = tid; j < N2; j += NT) {
         double rho[SS], v[SS], e[SS], T[SS], cs[SS], nd[SS], u2o[SS];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int s = 0; s < SS; s++) {
             if (s < S) {
                 const SpeciesConst sc = p.sp[s];
@@ -208,15 +210,15 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
             }
         }
         double x[SS], heat[SS];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int si = 0; si < SS; si++) { x[si] = (si < S) ? v[si] : 0.; heat[si] = 0.; }
         if (p.friction_solver == 0) {
             friction_analytic<SS>(p, S, dt, rho, v, T, nd, x, heat);
         } else {
         double A[SS][SS], M[SS][SS];
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int si = 0; si < SS; si++) {
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
             for (int sj = 0; sj < SS; sj++) {
                 if (si < S && sj < S)
                     A[si][sj] = p.fric_mask[si * S + sj] *
@@ -224,10 +226,10 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
                 else A[si][sj] = 0;
             }
         }
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int si = 0; si < SS; si++) {
             double rowsum = 0;
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
             for (int sj = 0; sj < SS; sj++) {
                 if (si < S && sj < S) { M[si][sj] = d_sub((si == sj) ? 1. : 0., d_mul(A[si][sj], dt)); rowsum = d_add(rowsum, A[si][sj]); }
                 else M[si][sj] = (si == sj) ? 1. : 0.;
@@ -235,11 +237,11 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
             M[si][si] = d_add(M[si][si], d_mul(dt, rowsum));
         }
         lu_solve<SS>(M, x, S);
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int si = 0; si < SS; si++) {
             if (si < S) {
                 double temp = 0;
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
                 for (int sj = 0; sj < SS; sj++) {
                     if (sj < S) {
                         const double v_end = x[si] - x[sj];
@@ -252,7 +254,7 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
             }
         }
         }
-#pragma unroll
+#pragma unroll (SS <= 8 ? SS : 1)
         for (int si = 0; si < SS; si++) {
             if (si < S) {
                 const SpeciesConst sc = p.sp[si];

@@ -50,6 +50,9 @@ CASES = {
     "f3_friction_3spc_an_mild": ("test_files/", "friction_3spc_an_mild.par", "friction_6spc.spc", [100, 1000]),
     # USE_PLANET_TEMPERATURE 1: the surface cell radiates at T_planet, slab model for T_planet (radiation.cpp:451-472,812-828)
     "t1_planetheating": ("runs_searth/", "SEarth_planetheating_1s1b.par", "mix3.spc", [100, 1000]),
+    # ten species through the numeric friction solver (the rolled 16-species instantiation of the kernel); our variant of the mild
+    # friction deck with the reference's 10-species file test2/mix_plt_radiationtest_multi.spc
+    "f4_friction_10spc_mild": ("test_files/", "friction_10spc_mild.par", "mix_plt_radiationtest_multi.spc", [100, 1000]),
     # DO_HYDRO 0: radiation-only relaxation (no hydro stages; at order 2 only the boundary conditions are applied,
     # advection.cpp:196-200; dt from the energy limiter, helpers.cpp:80-85), full FLD
     "n1_searth_nohydro": ("test2/", "SEarth_nohydro_1s1b.par", "mix_HHe.spc", [1, 100, 300]),

@@ -24,6 +24,7 @@ CASES = [
     ("f1_friction_2spc_an", 1, 1e-10), ("f1_friction_2spc_an", 100, 1e-8), ("f1_friction_2spc_an", 500, 1e-8),
     ("f2_friction_2spc_phys_an", 1, 1e-10), ("f2_friction_2spc_phys_an", 500, 1e-8), ("f3_friction_3spc_an_mild", 100, 1e-8), ("f3_friction_3spc_an_mild", 1000, 1e-8),
     ("t1_planetheating", 100, 1e-8), ("t1_planetheating", 1000, 1e-8),
+    ("f4_friction_10spc_mild", 100, 1e-8), ("f4_friction_10spc_mild", 1000, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8), ("c7_dynamic3_tabulated", 1000, 1e-8),
 ]
 
