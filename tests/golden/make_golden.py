@@ -53,6 +53,9 @@ CASES = {
     # ten species through the numeric friction solver (the rolled 16-species instantiation of the kernel); our variant of the mild
     # friction deck with the reference's 10-species file test2/mix_plt_radiationtest_multi.spc
     "f4_friction_10spc_mild": ("test_files/", "friction_10spc_mild.par", "mix_plt_radiationtest_multi.spc", [100, 1000]),
+    # PARI_SELF_GRAV_SWITCH 1: the constructor's 50-iteration relaxation loop (init_and_bounds.cpp:645-662) and
+    # update_mass_and_pot() every step / Heun stage (source.cpp:50-109); 2002 cells, full FLD
+    "g1_saturn_selfgrav2": ("runs_schulik2020/", "saturn_1grey_1s1b_selfgrav2.par", "mix_grey1e-2.spc", [100, 400]),
     # DO_HYDRO 0: radiation-only relaxation (no hydro stages; at order 2 only the boundary conditions are applied,
     # advection.cpp:196-200; dt from the energy limiter, helpers.cpp:80-85), full FLD
     "n1_searth_nohydro": ("test2/", "SEarth_nohydro_1s1b.par", "mix_HHe.spc", [1, 100, 300]),

@@ -25,6 +25,7 @@ CASES = [
     ("f2_friction_2spc_phys_an", 1, 1e-10), ("f2_friction_2spc_phys_an", 500, 1e-8), ("f3_friction_3spc_an_mild", 100, 1e-8), ("f3_friction_3spc_an_mild", 1000, 1e-8),
     ("t1_planetheating", 100, 1e-8), ("t1_planetheating", 1000, 1e-8),
     ("f4_friction_10spc_mild", 100, 1e-8), ("f4_friction_10spc_mild", 1000, 1e-8),
+    ("g1_saturn_selfgrav2", 100, 1e-8), ("g1_saturn_selfgrav2", 400, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8), ("c7_dynamic3_tabulated", 1000, 1e-8),
 ]
 
