@@ -117,6 +117,9 @@ struct DevParams {
     double T_star;
     double R_star, planet_semimajor, star_mass, UV_star, X_star, domain_min, domain_max;   // read by plugin hooks only
     double *Xstore;                     // full FLD: [ncol][N2][n][Bout+1]  X_i = S_i^-1 u_i and S_i^-1 rhs_i (rad_full.cuh)
+    // second-generation full FLD (rad_full2.cuh): per-cell coefficient stream [ncol][N2][NC], raw temperature solution
+    // [ncol][S][NP], and the surface cell's D_core [ncol][Bout] / incoming flux [ncol][Bin] for the planetary slab model
+    double *fcoef, *Tsol, *dcore, *ssurf;
     double *Tsave, *cssave;             // [ncol][S][NP] prim.temperature / prim.sound_speed as left by the post-hydro
                                         // compute_pressure: friction changes u but not these (source.cpp:485-505), and the
                                         // radiation solvers and the next CFL estimate read the stale values

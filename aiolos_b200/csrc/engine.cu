@@ -9,6 +9,7 @@
 #include "friction.cuh"
 #include "rad_simple.cuh"
 #include "rad_full.cuh"
+#include "rad_full2.cuh"
 #include "step2.cuh"
 #include <cmath>
 #include <cstring>
@@ -33,8 +34,10 @@ struct Engine::Impl {
     bool hydro_switch = false;      // deck runs (part of) its time with the hydro module off
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
     size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
-    bool full_reg = false;          // register-resident LU: measured slower (instruction-cache bound, profiles/r1g); option full_lu=reg
-              // full FLD: register-resident LU (k_rad_full<NB>); false = shared-memory LU
+    // full FLD: 2 = register-tiled LU, four kernels (rad_full2.cuh; default when n <= 24); 0 = first-generation shared-memory
+    // LU, one kernel (rad_full.cuh; option full_lu=smem, and n > 24); 1 = its shuffle-based register variant (full_lu=reg)
+    int full_mode = 0;
+    bool full2_ok = false; size_t smem_full2 = 0, smem_fasm = 0; int full_ri = 0;
     bool fused = false;             // single-species persistent step kernel (k_step1)
     int step1_ctas = 3;             // resident CTAs per SM the fused kernel is compiled for (3: 80 registers, 2: 128)
     int steps_per_launch = 16;
@@ -537,9 +540,10 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         if (k < 1 || k > 100000) throw std::invalid_argument("option steps_per_launch: expected 1..100000");
         im->steps_per_launch = k;
     } else if (key == "full_lu") {
-        if (value == "smem") im->full_reg = false;
-        else if (value == "reg") im->full_reg = true;
-        else throw std::invalid_argument("option full_lu: expected 'reg' or 'smem'");
+        if (value == "smem") im->full_mode = 0;
+        else if (value == "reg") im->full_mode = 1;
+        else if (value == "tile") { if (!im->full2_ok) throw std::invalid_argument("option full_lu=tile: needs PARI_USE_RADIATION 1 with at most 24 unknowns per cell"); im->full_mode = 2; }
+        else throw std::invalid_argument("option full_lu: expected 'tile', 'reg' or 'smem'");
     } else if (key == "step1_ctas") {
         if (value != "2" && value != "3") throw std::invalid_argument("option step1_ctas: expected 2 or 3");
         im->step1_ctas = std::stoi(value);

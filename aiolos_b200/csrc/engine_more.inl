@@ -14,18 +14,26 @@ void Engine::launch_friction() {
     else throw std::runtime_error("unsupported configuration: more than 16 species with friction");
 }
 
-// Full FLD (PARI_USE_RADIATION 1): one warp per column, two columns per CTA (rad_full.cuh).
+// Full FLD (PARI_USE_RADIATION 1): rad_full2.cuh (register-tiled LU, warp per column) when the block fits 24 unknowns, else the
+// first-generation kernel of rad_full.cuh (one warp per column, LU in shared memory).
 void Engine::full_setup() {
     DevParams& p = im->p;
-    p.Xstore = nullptr;
+    p.Xstore = nullptr; p.fcoef = nullptr; p.Tsol = nullptr; p.dcore = nullptr; p.ssurf = nullptr;
     if (p.use_rad_fluxes != 1) return;
     const FullDims fd = full_dims(p.Bout, p.S, p.Bin);
     if (fd.n > 32 || p.Bin > 32) throw std::runtime_error("unsupported configuration: full FLD with more than 32 unknowns per cell");
-    const size_t words = (size_t)p.ncol * p.N2 * fd.n * (p.Bout + 1);
+    const Full2Dims f2 = full2_dims(p.Bout, p.S);
+    im->full2_ok = fd.n <= 24;
+    size_t words = (size_t)p.ncol * p.N2 * fd.n * (p.Bout + 1);
+    size_t extra = 0;
+    if (im->full2_ok) {
+        words = std::max(words, (size_t)p.ncol * p.N2 * f2.XB);
+        extra = (size_t)p.ncol * p.N2 * f2.NC + (size_t)p.ncol * p.S * p.NP + (size_t)p.ncol * (p.Bout + p.Bin);
+    }
     size_t free_b = 0, total_b = 0;
 #ifndef AIO_EMU_BUILD
     CK(cudaMemGetInfo(&free_b, &total_b));
-    if (words * sizeof(double) > free_b * 9 / 10)
+    if ((words + extra) * sizeof(double) > free_b * 9 / 10)
         throw std::runtime_error("unsupported configuration: full FLD factor storage does not fit in HBM; use fewer columns per GPU");
 #endif
     p.Xstore = im->dalloc<double>(words);
@@ -42,12 +50,36 @@ void Engine::full_setup() {
     CK(cudaFuncSetAttribute(k_rad_full<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
     CK(cudaFuncSetAttribute(k_rad_full<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
     CK(cudaFuncSetAttribute(k_rad_full<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full));
+    if (im->full2_ok) {
+        p.fcoef = im->dalloc<double>((size_t)p.ncol * p.N2 * f2.NC);
+        p.Tsol = im->dalloc<double>((size_t)p.ncol * p.S * p.NP);
+        p.dcore = im->dalloc<double>((size_t)p.ncol * p.Bout);
+        p.ssurf = im->dalloc<double>((size_t)p.ncol * p.Bin);
+        im->full_ri = f2.RI;
+        im->smem_full2 = (size_t)f2.sm_warp * sizeof(double);
+        im->smem_fasm = (size_t)FULL_ASM_WARPS * 3 * p.S * p.Bout * sizeof(double);
+        CK(cudaFuncSetAttribute(k_full_lu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
+        CK(cudaFuncSetAttribute(k_full_lu<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
+        CK(cudaFuncSetAttribute(k_full_lu<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
+        CK(cudaFuncSetAttribute(k_full_asm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_fasm));
+        im->full_mode = 2;
+    }
 }
 void Engine::launch_full() {
     DevParams& p = im->p;
+    if (im->full_mode == 2) {
+        AIO_LAUNCH(k_full_heat, (p.ncol + 3) / 4, 128, 0, im->stream, p);
+        AIO_LAUNCH(k_full_asm, p.ncol, 32 * FULL_ASM_WARPS, im->smem_fasm, im->stream, p);
+        if (im->full_ri == 2) AIO_LAUNCH(k_full_lu<2>, p.ncol, 32, im->smem_full2, im->stream, p);
+        else if (im->full_ri == 4) AIO_LAUNCH(k_full_lu<4>, p.ncol, 32, im->smem_full2, im->stream, p);
+        else AIO_LAUNCH(k_full_lu<6>, p.ncol, 32, im->smem_full2, im->stream, p);
+        AIO_LAUNCH(k_full_post, p.ncol, 256, 0, im->stream, p);
+        im->launches += 3;
+        return;
+    }
     const int wpb = im->nt_full / 32;
     const int n = p.Bout + p.S, grid = (p.ncol + wpb - 1) / wpb;
-    if (!im->full_reg) AIO_LAUNCH(k_rad_full<0>, grid, im->nt_full, im->smem_full, im->stream, p);       // option full_lu=smem
+    if (im->full_mode == 0) AIO_LAUNCH(k_rad_full<0>, grid, im->nt_full, im->smem_full, im->stream, p);       // option full_lu=smem
     else if (n <= 8) AIO_LAUNCH(k_rad_full<8>, grid, im->nt_full, im->smem_full, im->stream, p);
     else if (n <= 16) AIO_LAUNCH(k_rad_full<16>, grid, im->nt_full, im->smem_full, im->stream, p);
     else if (n <= 24) AIO_LAUNCH(k_rad_full<24>, grid, im->nt_full, im->smem_full, im->stream, p);

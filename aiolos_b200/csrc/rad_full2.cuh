@@ -1,0 +1,658 @@
+// Full FLD solver (PARI_USE_RADIATION 1), second generation: the coupled J_b / T_s block-tridiagonal system of
+// update_fluxes_FLD (reference radiation.cpp:353-840) solved by block Thomas (block_tridiag_solve.h:57-130) with the
+// dense n x n LU of every cell held in REGISTERS.  Four launches per step:
+//
+//   k_full_heat   warp per column, lane = incoming band: reset_dS / update_dS in the reference's sequential top-down order
+//                 (radiation.cpp:15-348)
+//   k_full_asm    CTA per column, 8 warps over contiguous chunks of cells, lane = outgoing band: every coefficient of the
+//                 block rows (radiation.cpp:407-615) -- flux limiter, Planck fractions, matter coupling -- none of which
+//                 depends on the solve; written as a compact per-cell coefficient stream (diagonal, l, u, rhs, J-T / T-J
+//                 couplings: NC doubles instead of 3 n^2)
+//   k_full_lu     ONE WARP per column, the sequential part: per cell  S_i = d_i - l_i X_{i-1},  PartialPivLU(S_i) with the
+//                 augmented columns [u_i | rhs_i] riding along, back substitution  X_i = S_i^-1 u_i,  A_i = S_i^-1 (...),
+//                 then the back sweep  x_i = A_i - X_i x_{i+1}.
+//   k_full_post   CTA per column, thread per cell: negative-J scan, T clamp, e <- T, p <- e, cons <- prim, step tail.
+//
+// k_full_lu register tiling: the augmented matrix [S | u | rhs] (R x 2R, R = 4*RI >= n) is spread over the warp as a
+// 4 (row groups) x 8 (column groups) grid of lanes; lane (rg, cg) owns rows rg + 4 i and columns cg + 8 j (i, j < RI),
+// i.e. RI x RI doubles in registers (36 for configs[2], n = 23).  One elimination step k is a rank-1 update
+//   a[i][j] -= l[i] * pivotrow[j]
+// that costs each lane RI + RI shared-memory words (two broadcast buffers) for RI*RI FMAs: for configs[2] one 128-bit
+// shared load per 6 DFMA, against 2 LDS + 1 STS per DFMA in the first-generation kernel (rad_full.cuh).  The pivot
+// search runs lane = row on the published column with two REDUX.MAX (the IEEE bit pattern of |x| orders like an
+// unsigned integer) and a ballot for Eigen's first-maximum rule.  Finished pivot rows go straight to shared memory (U
+// transposed, forward-eliminated right-hand sides by row), where the back substitution -- lane = right-hand-side column,
+// the column in registers -- reads them; rows are never swapped back.  Every matrix element sees exactly the sequence of
+// roundings of Eigen's PartialPivLU / triangular solves (per element the updates are applied in increasing k, each as one
+// fused a - l*p, divisions are true divisions, a zero pivot column is not scaled, back substitution skips exactly-zero
+// unknowns: the all-zero T rows of the last ghost cell rely on that).
+//
+// Data movement: the coefficient stream and, in the back sweep, the X_i blocks are fetched two cells ahead with
+// cp.async.bulk (TMA 1-D bulk copy, completion on an mbarrier) so that the sequential sweep never waits on HBM.
+#pragma once
+#include "rad_full.cuh"
+
+namespace aio {
+
+struct Full2Dims {
+    int n, R, RI;
+    int NC;                        // doubles per cell in the coefficient stream (even => 16-byte blocks)
+    int o_D, o_L, o_U, o_B, o_JT, o_TJ, o_TT;
+    int LDXg, XB;                  // row stride (odd => conflict-free lane = row reads) and block size (even) of X_i in HBM
+    int LDU, LDY;
+    int sm_warp;                   // doubles of shared memory per column in k_full_lu
+    int o_col, o_l, o_prow, o_swap, o_UT, o_Y, o_coef, o_bar;      // forward-sweep carve-up
+    int o_ring, o_xs, o_stage;                                      // back-sweep carve-up (aliases the forward one)
+};
+__host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
+    Full2Dims d;
+    d.n = Bout + S;
+    d.RI = (d.n <= 8) ? 2 : (d.n <= 16) ? 4 : 6;
+    d.R = 4 * d.RI;
+    d.o_D = 0; d.o_L = d.R; d.o_U = 2 * d.R; d.o_B = 3 * d.R;
+    d.o_JT = 4 * d.R; d.o_TJ = d.o_JT + Bout * S; d.o_TT = d.o_TJ + S * Bout;
+    d.NC = d.o_TT + S * S; d.NC += d.NC & 1;
+    d.LDXg = (Bout + 1) | 1;
+    d.XB = d.n * d.LDXg; d.XB += d.XB & 1;
+    d.LDU = d.R + 2; d.LDY = d.R;
+    int o = 0;
+    d.o_col = o; o += 32;
+    d.o_l = o; o += d.R;
+    d.o_prow = o; o += 8 * d.RI;
+    d.o_swap = o; o += 8 * d.RI;
+    d.o_UT = o; o += d.R * d.LDU;
+    d.o_Y = o; o += d.R * d.LDY;
+    d.o_coef = o; o += 2 * d.NC;
+    d.o_bar = o; o += 4;
+    const int fwd = o;
+    o = 0;
+    d.o_ring = o; o += 2 * d.XB;
+    d.o_xs = o; o += 32;
+    d.o_stage = o; o += d.n * 8;
+    const int back = o;
+    // the mbarriers keep their place during the back sweep
+    d.sm_warp = (fwd > back + 4) ? fwd : back + 4;
+    if (back > d.o_bar) { d.o_bar = back; }
+    d.sm_warp += d.sm_warp & 1;
+    return d;
+}
+
+// ---- bulk-copy (TMA 1-D) + mbarrier helpers --------------------------------------------------------------------------------------
+#ifndef AIO_EMU_BUILD
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(double* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// one lane: arm the barrier with the byte count and start the copy global -> shared
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes, double* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(double* bar, unsigned parity) {
+    unsigned done = 0;
+    int spins = 0;
+    const unsigned a = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && ++spins > (1 << 24)) __trap();          // a lost copy must not hang the device
+    } while (!done);
+}
+__device__ __forceinline__ unsigned warp_umax(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned hi32(double x) { return (unsigned)__double2hiint(x); }
+__device__ __forceinline__ unsigned lo32(double x) { return (unsigned)__double2loint(x); }
+#else
+inline void mbar_init(double*, int) {}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async() {}
+inline void bulk_g2s(double* dst, const double* src, unsigned bytes, double*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(double*, unsigned) {}
+inline unsigned warp_umax(unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) { const int w = __shfl_xor_sync(0xffffffffu, (int)v, o); if ((unsigned)w > v) v = (unsigned)w; }
+    return v;
+}
+inline unsigned hi32(double x) { unsigned long long b; memcpy(&b, &x, 8); return (unsigned)(b >> 32); }
+inline unsigned lo32(double x) { unsigned long long b; memcpy(&b, &x, 8); return (unsigned)b; }
+#endif
+
+// ---- stellar heating: lane = incoming band, top-down exactly as radiation.cpp:51-63,154-348 -----------------------------------
+__global__ void __launch_bounds__(128) k_full_heat(DevParams p) {
+    __shared__ double contrib_all[4][MAXS * MAXB];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int col = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (col >= p.ncol) return;
+    const ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const double tnow = cst.t;
+    const int N = p.N, S = p.S, Bin = p.Bin;
+    double* contrib = contrib_all[wib];
+    const int b = lane;
+    double F = 0, rad_above = 0, top_prev = 0;
+    if (b < Bin) {
+        F = p.solar_heating_final[(size_t)col * Bin + b];
+        if (tnow < p.radiation_rampup_time)
+            F = F * (p.init_radiation_factor + (1. - p.init_radiation_factor) * tnow / p.radiation_rampup_time);
+        top_prev = p.dSband_top[(size_t)col * Bin + b];
+    }
+    for (int j = N + 1; j > 0; j--) {
+        const double dxj = __ldg(p.dx + j);
+        if (b < Bin) {
+            double tot = 0;
+            for (int s = 0; s < S; s++) tot += kapv(p, col, s, b, j) * p.u[idx_u(p, 0, col, s, j)];
+            const double cell_tau = tot * dxj;
+            const double rad_j = (j == N + 1) ? 0. : rad_above + cell_tau;
+            double dSb;
+            if (j < N + 1) {
+                const double Sb = F * exp(-rad_above);
+                if (j == p.ng - 1) p.ssurf[(size_t)col * Bin + b] = Sb;
+                dSb = 0.25 * Sb / dxj * (1. - p.bond_albedo);
+                const double dtau_tot = -(rad_above - rad_j);
+                double dS_he = dSb;
+                if (dtau_tot > 1e-3) dSb *= (-expm1(-dtau_tot));
+                else dSb *= (-fastexpm1_2(-dtau_tot));
+                dS_he *= -fastexpm1_2(-0.);
+                dSb -= dS_he;
+                dSb = smax(dSb, 0.);
+            } else {
+                dSb = top_prev;
+            }
+            if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
+            for (int s = 0; s < S; s++) {
+                const double hsw = p.highenergy_switch[s * Bin + b];
+                const double frac = hsw * kapv(p, col, s, b, j) * p.u[idx_u(p, 0, col, s, j)] * dxj / cell_tau;
+                contrib[s * Bin + b] = hsw * dSb * frac;
+            }
+            rad_above = rad_j;
+        }
+        __syncwarp();
+        if (lane < S) {
+            double acc = 0.;                              // reset_dS
+            for (int bb = 0; bb < Bin; bb++) { acc += contrib[lane * Bin + bb]; if (acc < 1e-50) acc = 0.; }
+            p.dS[idx_s(p, col, lane, j)] = acc;
+        }
+        __syncwarp();
+    }
+    if (lane < S) p.dS[idx_s(p, col, lane, 0)] = 0.;
+}
+
+// ---- block-row coefficients of every cell (radiation.cpp:407-615), parallel over cells -------------------------------------------
+// Per cell, NC doubles:  D[r] diagonal of d_i,  L[r] / U[r] the (diagonal) l_i / u_i entry of J row r,  B[r] right-hand side,
+// JT[b][s] = d_i(J_b, T_s),  TJ[s][b] = d_i(T_s, J_b),  TT[s][s'] off-diagonal T-T couplings (collisional heat exchange).
+constexpr int FULL_ASM_WARPS = 8;
+__global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p) {
+    AIO_DYN_SMEM(double, sm);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x;
+    const ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const double dt = cst.dt, tnow = cst.t;
+    const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin, Bout = p.Bout;
+    const Full2Dims fd = full2_dims(Bout, S);
+    const int n = fd.n;
+    // per warp: fac[S][Bout], dterm[S][Bout], rterm[S][Bout]
+    double* facs = sm + (size_t)w * 3 * S * Bout;
+    double* dterm = facs + S * Bout;
+    double* rterm = dterm + S * Bout;
+    const int CH = (N2 + FULL_ASM_WARPS - 1) / FULL_ASM_WARPS;
+    const int i0 = w * CH, i1 = min(N2, i0 + CH);
+    const bool isJ = lane < Bout, isT = (lane >= Bout && lane < n);
+    const int sT = lane - Bout;
+    auto total_opacity = [&](int j, int b) -> double {
+        if (j < 1 || j > N + 1) return 0.;
+        double tot = 0;
+        for (int s = 0; s < S; s++) tot = fmax(kapv(p, col, s, Bin + Bout + b, j) * p.u[idx_u(p, 0, col, s, j)], tot);
+        return tot;
+    };
+    auto Jold = [&](int j, int b) -> double { return (j >= 0 && j < N2) ? p.J[idx_J(p, col, b, j)] : 0.; };
+    auto Dcoef = [&](int i, int b, double Jc, double Jn, double toi, double toip) -> double {
+        const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+        const double rhokr = sqrt(toi * toip);
+        const double tau_inv = 1. / (dxc * rhokr);
+        const double R = p.xi_rad * tau_inv * fabs(Jn - Jc) / (Jc + 1e-300);
+        return 1. * tau_inv * 1. * __ldg(p.surf + i) * flux_limiter(R);
+    };
+    double D_prev = 0, to_i = 0, to_ip = 0, Jcur = 0, Jnext = 0;
+    if (isJ && i0 < i1) {
+        to_ip = total_opacity(i0, lane);
+        Jnext = Jold(i0, lane);
+        const int im = i0 - 1;
+        if (im >= 1 && im <= N) D_prev = Dcoef(im, lane, Jold(im, lane), Jnext, total_opacity(im, lane), to_ip);
+    }
+    for (int i = i0; i < i1; i++) {
+        double* cf = p.fcoef + ((size_t)col * N2 + i) * fd.NC;
+        // fac[s][b] = no_rad_trans * kappa_P * sigma T^3 / pi * planck fraction, and the T-row terms built from it
+        if (isJ && i <= N) {
+            for (int s = 0; s < S; s++) {
+                const SpeciesConst sc = p.sp[s];
+                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                const double fac = 1. * p.no_rad_trans * kapv(p, col, s, Bin + lane, i) * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
+                                   planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts);
+                facs[s * Bout + lane] = fac;
+                dterm[s * Bout + lane] = 16 * C_PI * fac / sc.cv;
+                rterm[s * Bout + lane] = 12 * C_PI * fac * Ts / sc.cv;
+                cf[fd.o_TJ + s * Bout + lane] = -4 * C_PI * kapv(p, col, s, Bin + lane, i) * p.no_rad_trans / sc.cv;
+            }
+        } else if (isJ) {
+            for (int s = 0; s < S; s++) cf[fd.o_TJ + s * Bout + lane] = 0.;
+        }
+        __syncwarp();
+        double l_rr = 0, u_rr = 0, rhs = 0, dd = 0;
+        if (isJ) {
+            const int b = lane;
+            Jcur = Jnext;
+            Jnext = (i + 1 < N2) ? Jold(i + 1, b) : 0.;
+            to_i = to_ip;
+            to_ip = total_opacity(i + 1, b);
+            double d = 0;
+            if (i >= 2 && i <= N + 1) { d = D_prev; l_rr = -D_prev; }
+            if (i <= N) {
+                const double tv = __ldg(p.vol + i) / (C_CLIGHT * dt);
+                d += tv;
+                rhs += tv * Jcur;
+            }
+            double D_i = 0;
+            if (i >= 1 && i <= N) {
+                D_i = Dcoef(i, b, Jcur, Jnext, to_i, to_ip);
+                u_rr = -D_i; d += D_i;
+            }
+            D_prev = D_i;
+            if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
+            if (i == p.ng - 1 && p.use_planetary_temperature) {      // surface cell radiates at T_planet (radiation.cpp:451-472)
+                const double Tp = cst.T_planet;
+                double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp));
+                if (Tp < 0) Ssrc *= -1;
+                const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+                double rhokr = smax(2. * (to_i * to_ip) / (to_i + to_ip), 4. / 3. / dxc);
+                rhokr = smin(0.5 * (to_i + to_ip), rhokr);
+                const double tau_inv = 1 / (dxc * rhokr);
+                const double R = p.xi_rad * tau_inv * fabs(Jnext - Jcur) / (Jnext + 1e-300);
+                const double Dc = flux_limiter(R) * tau_inv;
+                p.dcore[(size_t)col * Bout + b] = Dc;
+                const double Chi = 0.25;
+                const double sj = __ldg(p.surf + i);
+                l_rr = 0; d = 0.5 * (Dc + Chi) * sj; u_rr = -0.5 * (Dc - Chi) * sj; rhs = sj * Ssrc / (4 * C_PI);
+            }
+            if (p.closed_radiative_boundaries) {
+                if (i >= N2 - p.ng) { l_rr = -d; u_rr = 0; rhs = 0; }
+            } else if (i == N + 1) {
+                double f = __ldg(p.x_i12 + N) / __ldg(p.x_i12 + N + 1);
+                if (p.geometry == 0) f = 1;
+                else if (p.geometry == 2) f *= f;
+                l_rr = -f * d; u_rr = 0; rhs = 0;
+            }
+            const bool coupled = (i <= N && !(i < p.ng || i >= N + 2 - p.ng));
+            for (int s = 0; s < S; s++) {
+                double jt = 0.;
+                if (coupled) {
+                    const SpeciesConst sc = p.sp[s];
+                    const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                    Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                    const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                    const double fac = facs[s * Bout + b];
+                    const double vj = __ldg(p.vol + i);
+                    d += vj * q.rho * kapv(p, col, s, Bin + b, i) * p.no_rad_trans;
+                    jt = -4 * vj * q.rho * fac;
+                    rhs -= 3 * vj * q.rho * fac * Ts;
+                }
+                cf[fd.o_JT + b * S + s] = jt;
+            }
+            dd = d;
+        } else if (isT) {
+            const int s = sT;
+            for (int sj = 0; sj < S; sj++) cf[fd.o_TT + s * S + sj] = 0.;
+            if (i <= N) {
+                const SpeciesConst sc = p.sp[s];
+                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                double d = 1 / dt;
+                rhs = Ts / dt;
+                rhs += (p.dS[idx_s(p, col, s, i)] + 0.) / u1 / sc.cv;
+                for (int b = 0; b < Bout; b++) {
+                    d += dterm[s * Bout + b];
+                    rhs += rterm[s * Bout + b];
+                }
+                // collisional T_i - T_j coupling (radiation.cpp:589-615, source.cpp:656-674)
+                if (p.use_collisional_heating && S > 1) {
+                    double tot0 = 0;
+                    if (i >= 1) for (int ss = 0; ss < S; ss++) tot0 = fmax(kapv(p, col, ss, Bin + Bout + 0, i) * p.u[idx_u(p, 0, col, ss, i)], tot0);
+                    const double tau = tot0 * (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+                    const double damp = (tau < 1e3) ? 1. : 1.e-4;
+                    double diag_sum = 0, self = 0;
+                    for (int sj = 0; sj < S; sj++) {
+                        const SpeciesConst cj = p.sp[sj];
+                        const double w1 = p.u[idx_u(p, 0, col, sj, i)], w2 = p.u[idx_u(p, 1, col, sj, i)], w3 = p.u[idx_u(p, 2, col, sj, i)];
+                        Prim3 qj = cons_to_prim(w1, w2, w3, cj.gm1);
+                        const double Tj = p.Tsave ? p.Tsave[idx_s(p, col, sj, i)] : eint_of(qj.p, qj.rho, cj.gm1) / cj.cv;
+                        double fc = p.fric_mask[s * S + sj] * alpha_pair(p, s, sj, S, sc, cj, u1, w1, w1 / cj.mass, Ts, Tj, tnow);
+                        fc *= 3 * C_KB / (sc.cv * (sc.mass + cj.mass));
+                        diag_sum += fc;
+                        if (sj == s) self = fc;
+                        else cf[fd.o_TT + s * S + sj] = 0. - fc * damp;
+                    }
+                    d -= (self - diag_sum) * damp;
+                }
+                dd = d;
+            }
+        }
+        if (lane < fd.R) {
+            cf[fd.o_D + lane] = dd;
+            cf[fd.o_L + lane] = l_rr;
+            cf[fd.o_U + lane] = u_rr;
+            cf[fd.o_B + lane] = rhs;
+        }
+        if (lane == 0 && ((fd.o_TT + S * S) & 1)) cf[fd.NC - 1] = 0.;
+        __syncwarp();
+    }
+}
+
+// ---- the sequential sweep: one warp per column, LU in registers ---------------------------------------------------------------------
+template <int RI>
+struct LuCtx {
+    static constexpr int R = 4 * RI, LDU = R + 2, LDY = R;      // same numbers as full2_dims(); compile-time here
+    double* colb; double* lb; double* prow; double* swp; double* UT; double* Y;
+    int n, rg, cg, lane;
+};
+
+// Elimination steps k = 4Q .. 4Q+3: rows of local index < Q and column blocks < Q/2 are finished (dead registers).
+template <int RI, int Q>
+__device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c) {
+    constexpr int JK = Q / 2;          // local column block that holds column k
+    constexpr int LB = RI / 2;         // column blocks of the LU part; blocks LB.. are the right-hand sides
+    const int lane = c.lane, rg = c.rg, cg = c.cg;
+#pragma unroll 1
+    for (int kk = 0; kk < 4; kk++) {
+        const int k = 4 * Q + kk;
+        if (k >= c.n) break;
+        const int cgk = 4 * (Q & 1) + kk;
+        // 1. publish column k (live rows only)
+        if (cg == cgk) {
+#pragma unroll
+            for (int i = Q; i < RI; i++) c.colb[rg + 4 * i] = a[i][JK];
+        }
+        __syncwarp();
+        // 2. pivot search, lane = row: first row holding the largest |a(r,k)|, r >= k  (PartialPivLU)
+        const double v = c.colb[lane < 4 * RI ? lane : 0];
+        const bool cand = (lane >= k) && (lane < c.n);
+        const double av = fabs(v);
+        const unsigned hk = cand ? hi32(av) + 1u : 0u;
+        const unsigned mh = warp_umax(hk);
+        const bool top = cand && (hk == mh);
+        const unsigned lk = top ? lo32(av) : 0u;
+        const unsigned ml = warp_umax(lk);
+        const unsigned votes = __ballot_sync(0xffffffffu, top && (lk == ml));
+        const int piv = __ffs(votes) - 1;
+        const bool nonzero = !(mh == 1u && ml == 0u);
+        // 3. multipliers; after the row exchange position piv holds the old row k
+        const double pv = c.colb[piv];
+        const double vk = c.colb[k];
+        const double mine = (lane == piv) ? vk : v;
+        const double l = nonzero ? mine / pv : mine;
+        if (lane < 4 * RI) c.lb[(lane & 3) * RI + (lane >> 2)] = l;
+        // 4. the pivot row becomes row k of U and of the forward-eliminated right-hand sides; broadcast copy for the update
+        const int ip = piv >> 2, rgp = piv & 3;
+        if (rg == rgp) {
+#pragma unroll
+            for (int i = Q; i < RI; i++)
+                if (i == ip) {          // ip is warp-uniform: a branch, the stores read the registers of row i directly
+#pragma unroll
+                    for (int j = JK; j < RI; j++) c.prow[cg * RI + j] = a[i][j];
+#pragma unroll
+                    for (int j = JK; j < LB; j++) c.UT[(cg + 8 * j) * c.LDU + k] = a[i][j];
+#pragma unroll
+                    for (int j = LB; j < RI; j++) c.Y[k * c.LDY + cg + 8 * (j - LB)] = a[i][j];
+                }
+        }
+        // 5. the old row k (lanes rg == kk, local row Q) moves to position piv
+        const bool swap = (piv != k);
+        if (swap && rg == kk) {
+#pragma unroll
+            for (int j = JK; j < RI; j++) c.swp[cg * RI + j] = a[Q][j];
+        }
+        __syncwarp();
+        if (swap && rg == rgp) {
+#pragma unroll
+            for (int i = Q; i < RI; i++)
+                if (i == ip) {
+#pragma unroll
+                    for (int j = JK; j < RI; j++) a[i][j] = c.swp[cg * RI + j];
+                }
+        }
+        // 6. rank-1 update of the live block
+        double lv[RI], pr[RI];
+#pragma unroll
+        for (int i = Q; i < RI; i++) lv[i] = c.lb[rg * RI + i];
+#pragma unroll
+        for (int j = JK; j < RI; j++) pr[j] = c.prow[cg * RI + j];
+#pragma unroll
+        for (int i = Q; i < RI; i++) {
+#pragma unroll
+            for (int j = JK; j < RI; j++) a[i][j] = d_fnma(lv[i], pr[j], a[i][j]);
+        }
+    }
+}
+
+template <int RI>
+__global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p) {
+    AIO_DYN_SMEM(double, sm);
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x;
+    const ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const int N2 = p.N2, S = p.S, Bout = p.Bout;
+    const Full2Dims fd = full2_dims(Bout, S);
+    const int n = fd.n;
+    constexpr int R = 4 * RI, LB = RI / 2;
+    LuCtx<RI> c;
+    c.colb = sm + fd.o_col; c.lb = sm + fd.o_l; c.prow = sm + fd.o_prow; c.swp = sm + fd.o_swap;
+    c.UT = sm + fd.o_UT; c.Y = sm + fd.o_Y; c.n = n;
+    c.rg = lane >> 3; c.cg = lane & 7; c.lane = lane;
+    const int rg = c.rg, cg = c.cg;
+    double* coefs = sm + fd.o_coef;
+    double* bars = sm + fd.o_bar;                  // [0,1]: coefficient ring, [2,3]: X ring of the back sweep
+    const double* cf_g = p.fcoef + (size_t)col * N2 * fd.NC;
+    double* Xg = p.Xstore + (size_t)col * N2 * fd.XB;
+    const unsigned coef_bytes = (unsigned)(fd.NC * sizeof(double)), x_bytes = (unsigned)(fd.XB * sizeof(double));
+
+    if (lane == 0) { for (int q = 0; q < 4; q++) mbar_init(bars + q, 1); fence_mbar_init(); }
+    for (int q = lane; q < R * fd.LDY; q += 32) c.Y[q] = 0.;
+    __syncwarp();
+    if (lane == 0) {
+        bulk_g2s(coefs, cf_g, coef_bytes, bars + 0);
+        if (N2 > 1) bulk_g2s(coefs + fd.NC, cf_g + fd.NC, coef_bytes, bars + 1);
+    }
+
+    // ---- forward sweep ------------------------------------------------------------------------------------------------------------
+    for (int i = 0; i < N2; i++) {
+        const int slot = i & 1;
+        mbar_wait(bars + slot, (unsigned)((i >> 1) & 1));
+        const double* cf = coefs + slot * fd.NC;
+        double a[RI][RI];
+        // assemble this lane's RI x RI piece of [S_i | u_i | rhs_i],  S_i = d_i - l_i X_{i-1}   (X_{i-1}, A_{i-1} live in Y)
+#pragma unroll
+        for (int ii = 0; ii < RI; ii++) {
+            const int r = rg + 4 * ii;
+            const bool rowJ = r < Bout, rowT = (r >= Bout && r < n);
+            const double Dr = cf[fd.o_D + r], Lr = cf[fd.o_L + r], Ur = cf[fd.o_U + r], Br = cf[fd.o_B + r];
+            const bool useX = rowJ && (i > 0) && (Lr != 0.);
+#pragma unroll
+            for (int j = 0; j < LB; j++) {
+                const int cc = cg + 8 * j;
+                double val = 0.;
+                if (rowJ) {
+                    if (cc < Bout) {
+                        val = (cc == r) ? Dr : 0.;
+                        if (useX) val = d_sub(val, d_mul(Lr, c.Y[r * c.LDY + cc]));
+                    } else if (cc < n) val = cf[fd.o_JT + r * S + (cc - Bout)];
+                } else if (rowT) {
+                    if (cc < Bout) val = cf[fd.o_TJ + (r - Bout) * Bout + cc];
+                    else if (cc < n) val = (cc == r) ? Dr : cf[fd.o_TT + (r - Bout) * S + (cc - Bout)];
+                }
+                a[ii][j] = val;
+            }
+#pragma unroll
+            for (int j = LB; j < RI; j++) {
+                const int cc = cg + 8 * (j - LB);
+                double val = 0.;
+                if (r < n) {
+                    if (cc < Bout) val = (cc == r) ? Ur : 0.;
+                    else if (cc == Bout) {
+                        val = Br;
+                        if (useX) val = d_sub(val, d_mul(Lr, c.Y[r * c.LDY + Bout]));
+                    }
+                }
+                a[ii][j] = val;
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && i + 2 < N2) bulk_g2s(coefs + slot * fd.NC, cf_g + (size_t)(i + 2) * fd.NC, coef_bytes, bars + slot);
+
+        lu_phase<RI, 0>(a, c);
+        lu_phase<RI, 1>(a, c);
+        if constexpr (RI > 2) { lu_phase<RI, 2>(a, c); lu_phase<RI, 3>(a, c); }
+        if constexpr (RI > 4) { lu_phase<RI, 4>(a, c); lu_phase<RI, 5>(a, c); }
+        __syncwarp();
+
+        // ---- back substitution with U, lane = right-hand-side column (Bout columns of u_i and the rhs): x stays in registers ----
+        if (lane <= Bout) {
+            double y[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) y[k] = (k < n) ? c.Y[k * c.LDY + lane] : 0.;
+#pragma unroll
+            for (int k = R - 1; k >= 0; k--) {
+                if (k < n) {
+                    const double* uk = c.UT + k * c.LDU;            // column k of U, contiguous: 16-byte aligned (LDU even)
+                    const double2* uk2 = reinterpret_cast<const double2*>(uk);
+                    const bool nz = (y[k] != 0.);
+                    const double z = nz ? y[k] / uk[k] : y[k];
+                    y[k] = z;
+#pragma unroll
+                    for (int r = 0; r < k; r += 2) {
+                        const double2 uu = uk2[r >> 1];
+                        y[r] = d_fnma(z, uu.x, y[r]);
+                        if (r + 1 < k) y[r + 1] = d_fnma(z, uu.y, y[r + 1]);
+                    }
+                }
+            }
+            double* Xi = Xg + (size_t)i * fd.XB;
+#pragma unroll
+            for (int k = 0; k < R; k++)
+                if (k < n) { c.Y[k * c.LDY + lane] = y[k]; Xi[k * fd.LDXg + lane] = y[k]; }
+        }
+        __syncwarp();
+    }
+
+    // ---- back sweep  x_i = A_i - X_i x_{i+1}  (lane = row), solution staged eight cells at a time ------------------------------------
+#ifndef AIO_EMU_BUILD
+    __threadfence_block();
+#endif
+    fence_proxy_async();
+    __syncwarp();
+    double* ring = sm + fd.o_ring;
+    double* xs = sm + fd.o_xs;
+    double* stage = sm + fd.o_stage;
+    if (lane == 0) {
+        // the X blocks were written by this warp with ordinary stores: they are visible to the bulk copy after the fence above
+        bulk_g2s(ring, Xg + (size_t)(N2 - 1) * fd.XB, x_bytes, bars + 2);
+        if (N2 > 1) bulk_g2s(ring + fd.XB, Xg + (size_t)(N2 - 2) * fd.XB, x_bytes, bars + 3);
+    }
+    for (int q = 0; q < N2; q++) {
+        const int i = N2 - 1 - q, slot = q & 1;
+        mbar_wait(bars + 2 + slot, (unsigned)((q >> 1) & 1));
+        const double* Xi = ring + slot * fd.XB;
+        double x = 0;
+        if (lane < n) {
+            x = Xi[lane * fd.LDXg + Bout];
+            if (q > 0) {
+                double t = 0;
+                for (int cc = 0; cc < Bout; cc++) t += Xi[lane * fd.LDXg + cc] * xs[cc];
+                x = x - t;
+            }
+        }
+        __syncwarp();
+        if (lane < n) { xs[lane] = x; stage[lane * 8 + (i & 7)] = x; }
+        __syncwarp();
+        if (lane == 0 && q + 2 < N2) bulk_g2s(ring + slot * fd.XB, Xg + (size_t)(i - 2) * fd.XB, x_bytes, bars + 2 + slot);
+        if ((i & 7) == 0 || false) {
+            // flush cells i .. min(i+7, N2-1): J rows to Jrad_FLD, T rows to the temperature solution (both raw, see k_full_post)
+            const int cnt = min(8, N2 - i);
+            for (int e = lane; e < n * 8; e += 32) {
+                const int r = e >> 3, o = e & 7;
+                if (o < cnt) {
+                    const double val = stage[r * 8 + o];
+                    if (r < Bout) p.J[idx_J(p, col, r, i + o)] = val;
+                    else p.Tsol[idx_s(p, col, r - Bout, i + o)] = val;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- negative-J scan, T clamp, e <- T, p <- e, cons <- prim, step tail (radiation.cpp:782-838, advection.cpp:282-346) ----------------
+__global__ void __launch_bounds__(256) k_full_post(DevParams p) {
+    __shared__ double red[32];
+    __shared__ double rmin[32];
+    const int col = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const double dt = cst.dt;
+    const int N = p.N, N2 = p.N2, S = p.S, Bout = p.Bout;
+    TailAcc acc; acc.minstep = 0; acc.maxde = 0; acc.bad = 0; acc.badval = 0;
+    int negJ = 0; double negJval = 1e308;
+    for (int i = tid; i < N2; i += NT) {
+        for (int b = 0; b < Bout; b++) {
+            const double Jv = p.J[idx_J(p, col, b, i)];
+            if (p.couple_J_into_T && i <= N - 1 && Jv < 0) {           // advection.cpp:308-338
+                if (Jv > -1e-10) p.J[idx_J(p, col, b, i)] = Jv * -1.;
+                else if (!(i < N && p.use_planetary_temperature && p.J[idx_J(p, col, b, N)] > 0)) { negJ = 1; negJval = fmin(negJval, Jv); }
+            }
+        }
+        for (int s = 0; s < S; s++) {
+            const SpeciesConst sc = p.sp[s];
+            double T = p.Tsol[idx_s(p, col, s, i)];
+            if (T < p.temperature_floor) T = p.temperature_floor;
+            if (T > p.max_temperature) T = p.max_temperature;
+            const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+            Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+            const double e_old = eint_of(q.p, q.rho, sc.gm1);
+            const double cs_old = p.cssave ? p.cssave[idx_s(p, col, s, i)] : cs_of(e_old, sc.gm1);
+            const double e = T * sc.cv;
+            q.p = e * q.rho * sc.gm1;
+            double n1, n2, n3;
+            prim_to_cons(q, sc.gm1, n1, n2, n3);
+            p.u[idx_u(p, 0, col, s, i)] = n1; p.u[idx_u(p, 1, col, s, i)] = n2; p.u[idx_u(p, 2, col, s, i)] = n3;
+            tail_cell(p, col, s, i, q.v, cs_old, e, T, acc);
+        }
+    }
+    const double ms = block_max(acc.minstep, red), md = block_max(acc.maxde, red);
+    const int bad = block_or(acc.bad), nj = block_or(negJ);
+    const double njv = -block_max(-negJval, rmin);
+    __syncthreads();
+    if (tid == 0) {
+        // slab model of the planet's surface temperature (radiation.cpp:812-828), bands summed in order
+        if (p.use_planetary_temperature) {
+            double F = 0, S_surf = 0;
+            for (int b = 0; b < Bout; b++) {
+                F -= 4 * C_PI * p.dcore[(size_t)col * Bout + b] * (p.J[idx_J(p, col, b, p.ng)] - p.J[idx_J(p, col, b, p.ng - 1)]);
+                S_surf += 0.25 * p.ssurf[(size_t)col * p.Bin + b];
+            }
+            const double S_tot = S_surf - F + C_SIGMA_RAD * (p.T_int * p.T_int) * (p.T_int * p.T_int);
+            double Tp = cst.T_planet;
+            if (p.core_cv > 0) { const double denom = 4 * C_SIGMA_RAD * Tp * Tp * Tp + p.core_cv / dt; Tp += S_tot / denom; }
+            else Tp = pow(pow(Tp, 4) + S_tot / C_SIGMA_RAD, 0.25);
+            cst.T_planet = Tp;
+        }
+        cst.minstep = ms; cst.maxde = md;
+        cst.steps += 1;
+        if (bad) { cst.status = COL_NEG_T; cst.t = 1.1 * cst.t_max; }
+        else if (nj) { cst.status = COL_NEG_J; cst.crash_value = njv; cst.t = 1.1 * cst.t_max; }
+    }
+}
+
+}  // namespace aio

@@ -16,8 +16,12 @@ ap.add_argument("--ncols", type=int, default=4096)
 ap.add_argument("--spinup", type=int, default=600)
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--bytes", type=float, default=0.0, help="algorithmic bytes per cell-species-update (SURVEY 8d)")
+ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
 a = ap.parse_args()
 ens = A.Ensemble.from_dump(os.path.join(ROOT, "tests", "golden", f"{a.case}_init.bin"), ncols=a.ncols)
+for kv in a.opt:
+    k_, v_ = kv.split("=", 1)
+    ens.set_option(k_, v_)
 ens.advance(a.spinup)
 s0 = ens.total_steps
 ms = ens.advance(a.steps, timed=True)
@@ -26,7 +30,7 @@ upd = cs * ens.num_cells * ens.num_species
 kt = ens.kernel_times(min(a.steps, 10))
 out = {"case": a.case, "ncols": a.ncols, "num_cells": ens.num_cells, "num_species": ens.num_species, "steps": a.steps,
        "ms_per_step": ms / a.steps, "updates_per_s": upd / (ms * 1e-3), "kernel_ms": kt,
-       "state": ens.status(0)}
+       "state": ens.status(0), "options": a.opt}
 if a.bytes:
     out["hbm_frac_of_6536GBs"] = out["updates_per_s"] * a.bytes / 6536.4e9
 print(json.dumps(out))
