@@ -9,7 +9,8 @@
 #include "friction.cuh"
 #include "rad_simple.cuh"
 #include "rad_full.cuh"
-#include "rad_full2.cuh"
+#include "rad_full2.h"
+#include "cuda_check.h"
 #include "step2.cuh"
 #include <cmath>
 #include <cstring>
@@ -17,9 +18,6 @@
 
 namespace aio {
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    std::ostringstream os_; os_ << "CUDA error " << cudaGetErrorString(e_) << " at " << __FILE__ << ":" << __LINE__; \
-    throw std::runtime_error(os_.str()); } } while (0)
 
 struct Engine::Impl {
     DevParams p{};

@@ -58,22 +58,14 @@ void Engine::full_setup() {
         im->full_ri = f2.RI;
         im->smem_full2 = (size_t)f2.sm_warp * sizeof(double);
         im->smem_fasm = (size_t)FULL_ASM_WARPS * 3 * p.S * p.Bout * sizeof(double);
-        CK(cudaFuncSetAttribute(k_full_lu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
-        CK(cudaFuncSetAttribute(k_full_lu<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
-        CK(cudaFuncSetAttribute(k_full_lu<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_full2));
-        CK(cudaFuncSetAttribute(k_full_asm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)im->smem_fasm));
+        full2_configure(im->full_ri, im->smem_full2, im->smem_fasm);
         im->full_mode = 2;
     }
 }
 void Engine::launch_full() {
     DevParams& p = im->p;
     if (im->full_mode == 2) {
-        AIO_LAUNCH(k_full_heat, (p.ncol + 3) / 4, 128, 0, im->stream, p);
-        AIO_LAUNCH(k_full_asm, p.ncol, 32 * FULL_ASM_WARPS, im->smem_fasm, im->stream, p);
-        if (im->full_ri == 2) AIO_LAUNCH(k_full_lu<2>, p.ncol, 32, im->smem_full2, im->stream, p);
-        else if (im->full_ri == 4) AIO_LAUNCH(k_full_lu<4>, p.ncol, 32, im->smem_full2, im->stream, p);
-        else AIO_LAUNCH(k_full_lu<6>, p.ncol, 32, im->smem_full2, im->stream, p);
-        AIO_LAUNCH(k_full_post, p.ncol, 256, 0, im->stream, p);
+        full2_launch(p, im->full_ri, im->smem_full2, im->smem_fasm, (void*)im->stream);
         im->launches += 3;
         return;
     }

@@ -538,6 +538,7 @@ __device__ __forceinline__ StepInfo step_head(const DevParams& p, const int col)
 // ones.  When the nine work arrays do not fit in shared memory they are taken from the column's HBM scratch area instead (the
 // code below only ever touches them between __syncthreads(), with plain loads and stores).
 template <int CPT, int NTB = 256>
+#ifndef AIO_NO_SHARED_KERNELS      // defined by the translation units that only borrow the device functions
 __global__ void __launch_bounds__(NTB, NTB == 256 ? 2 : 1) k_hydro(DevParams p) {
     AIO_DYN_SMEM(double, sm_dyn);
     const int col = blockIdx.x;
@@ -548,6 +549,7 @@ __global__ void __launch_bounds__(NTB, NTB == 256 ? 2 : 1) k_hydro(DevParams p) 
     hydro_phase<CPT>(p, col, sm, si.dt, si.t_old, si.snap, acc);
     if (p.last_kernel == 0) tail_commit(p, col, acc, sm + 9 * p.N2);
 }
+#endif
 
 // Initial values of the dt inputs (what c_Sim's ctor + first get_cfl_timestep() see: init_and_bounds.cpp:678-682).
 __global__ void k_prime(DevParams p) {

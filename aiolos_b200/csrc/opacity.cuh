@@ -88,6 +88,7 @@ __device__ inline double interpol_tabulated_opacity(const DevParams& p, const Op
 }
 
 // update_opacities for every species and cell of one column: CTA per column, thread per cell
+#ifndef AIO_NO_SHARED_KERNELS      // defined by the translation units that only borrow the device functions
 __global__ void __launch_bounds__(256) k_opacity(DevParams p) {
     const int col = blockIdx.x;
     const ColState& c = p.cs[col];
@@ -126,5 +127,6 @@ __global__ void __launch_bounds__(256) k_opacity(DevParams p) {
         }
     }
 }
+#endif
 
 }  // namespace aio

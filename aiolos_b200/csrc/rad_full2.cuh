@@ -31,51 +31,9 @@
 // cp.async.bulk (TMA 1-D bulk copy, completion on an mbarrier) so that the sequential sweep never waits on HBM.
 #pragma once
 #include "rad_full.cuh"
+#include "rad_full2.h"
 
 namespace aio {
-
-struct Full2Dims {
-    int n, R, RI;
-    int NC;                        // doubles per cell in the coefficient stream (even => 16-byte blocks)
-    int o_D, o_L, o_U, o_B, o_JT, o_TJ, o_TT;
-    int LDXg, XB;                  // row stride (odd => conflict-free lane = row reads) and block size (even) of X_i in HBM
-    int LDU, LDY;
-    int sm_warp;                   // doubles of shared memory per column in k_full_lu
-    int o_col, o_l, o_prow, o_swap, o_UT, o_Y, o_coef, o_bar;      // forward-sweep carve-up
-    int o_ring, o_xs, o_stage;                                      // back-sweep carve-up (aliases the forward one)
-};
-__host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
-    Full2Dims d;
-    d.n = Bout + S;
-    d.RI = (d.n <= 8) ? 2 : (d.n <= 16) ? 4 : 6;
-    d.R = 4 * d.RI;
-    d.o_D = 0; d.o_L = d.R; d.o_U = 2 * d.R; d.o_B = 3 * d.R;
-    d.o_JT = 4 * d.R; d.o_TJ = d.o_JT + Bout * S; d.o_TT = d.o_TJ + S * Bout;
-    d.NC = d.o_TT + S * S; d.NC += d.NC & 1;
-    d.LDXg = (Bout + 1) | 1;
-    d.XB = d.n * d.LDXg; d.XB += d.XB & 1;
-    d.LDU = d.R + 2; d.LDY = d.R;
-    int o = 0;
-    d.o_col = o; o += 32;
-    d.o_l = o; o += d.R;
-    d.o_prow = o; o += 8 * d.RI;
-    d.o_swap = o; o += 8 * d.RI;
-    d.o_UT = o; o += d.R * d.LDU;
-    d.o_Y = o; o += d.R * d.LDY;
-    d.o_coef = o; o += 2 * d.NC;
-    d.o_bar = o; o += 4;
-    const int fwd = o;
-    o = 0;
-    d.o_ring = o; o += 2 * d.XB;
-    d.o_xs = o; o += 32;
-    d.o_stage = o; o += d.n * 8;
-    const int back = o;
-    // the mbarriers keep their place during the back sweep
-    d.sm_warp = (fwd > back + 4) ? fwd : back + 4;
-    if (back > d.o_bar) { d.o_bar = back; }
-    d.sm_warp += d.sm_warp & 1;
-    return d;
-}
 
 // ---- bulk-copy (TMA 1-D) + mbarrier helpers --------------------------------------------------------------------------------------
 #ifndef AIO_EMU_BUILD
@@ -103,6 +61,8 @@ __device__ __forceinline__ void mbar_wait(double* bar, unsigned parity) {
 }
 __device__ __forceinline__ unsigned warp_umax(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ unsigned hi32(double x) { return (unsigned)__double2hiint(x); }
+// keeps the compiler from hoisting a select across a division (it would divide the raw operands and select afterwards)
+__device__ __forceinline__ void opaque(double& x) { asm volatile("" : "+d"(x)); }
 __device__ __forceinline__ unsigned lo32(double x) { return (unsigned)__double2loint(x); }
 #else
 inline void mbar_init(double*, int) {}
@@ -115,6 +75,7 @@ inline unsigned warp_umax(unsigned v) {
     return v;
 }
 inline unsigned hi32(double x) { unsigned long long b; memcpy(&b, &x, 8); return (unsigned)(b >> 32); }
+inline void opaque(double&) {}
 inline unsigned lo32(double x) { unsigned long long b; memcpy(&b, &x, 8); return (unsigned)b; }
 #endif
 
@@ -181,7 +142,6 @@ __global__ void __launch_bounds__(128) k_full_heat(DevParams p) {
 // ---- block-row coefficients of every cell (radiation.cpp:407-615), parallel over cells -------------------------------------------
 // Per cell, NC doubles:  D[r] diagonal of d_i,  L[r] / U[r] the (diagonal) l_i / u_i entry of J row r,  B[r] right-hand side,
 // JT[b][s] = d_i(J_b, T_s),  TJ[s][b] = d_i(T_s, J_b),  TT[s][s'] off-diagonal T-T couplings (collisional heat exchange).
-constexpr int FULL_ASM_WARPS = 8;
 __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -391,10 +351,18 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
         // 3. multipliers; after the row exchange position piv holds the old row k
         const double pv = c.colb[piv];
         const double vk = c.colb[k];
+        // Rows k+1 .. n-1 are live.  Zero entries (structural zeros of the blocks are common) and dead lanes must not reach
+        // the division: a zero numerator sends the whole warp through the IEEE slow path of the FP64 division (ncu r2b: 22 %
+        // of all executed instructions).  0 / pv = 0, so they bypass it.
         const double mine = (lane == piv) ? vk : v;
-        const double l = nonzero ? mine / pv : mine;
+        const bool live = (lane > k) && (lane < c.n);
+        const bool divide = live && nonzero && (mine != 0.);
+        double num = divide ? mine : 1., den = divide ? pv : 1.;
+        opaque(num); opaque(den);
+        const double q = num / den;
+        const double l = divide ? q : (live ? mine : 0.);
         if (lane < 4 * RI) c.lb[(lane & 3) * RI + (lane >> 2)] = l;
-        // 4. the pivot row becomes row k of U and of the forward-eliminated right-hand sides; broadcast copy for the update
+        // 4. broadcast copy of the pivot row for the update (it becomes row k of U and of the eliminated right-hand sides in 6.)
         const int ip = piv >> 2, rgp = piv & 3;
         if (rg == rgp) {
 #pragma unroll
@@ -402,10 +370,6 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
                 if (i == ip) {          // ip is warp-uniform: a branch, the stores read the registers of row i directly
 #pragma unroll
                     for (int j = JK; j < RI; j++) c.prow[cg * RI + j] = a[i][j];
-#pragma unroll
-                    for (int j = JK; j < LB; j++) c.UT[(cg + 8 * j) * c.LDU + k] = a[i][j];
-#pragma unroll
-                    for (int j = LB; j < RI; j++) c.Y[k * c.LDY + cg + 8 * (j - LB)] = a[i][j];
                 }
         }
         // 5. the old row k (lanes rg == kk, local row Q) moves to position piv
@@ -423,12 +387,19 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
                     for (int j = JK; j < RI; j++) a[i][j] = c.swp[cg * RI + j];
                 }
         }
-        // 6. rank-1 update of the live block
+        // 6. rank-1 update of the live block; one row group files the pivot row: U transposed (column k of U is read
+        //    contiguously by the back substitution), forward-eliminated right-hand sides by row
         double lv[RI], pr[RI];
 #pragma unroll
         for (int i = Q; i < RI; i++) lv[i] = c.lb[rg * RI + i];
 #pragma unroll
         for (int j = JK; j < RI; j++) pr[j] = c.prow[cg * RI + j];
+        if (rg == kk) {
+#pragma unroll
+            for (int j = JK; j < LB; j++) c.UT[(cg + 8 * j) * c.LDU + k] = pr[j];
+#pragma unroll
+            for (int j = LB; j < RI; j++) c.Y[k * c.LDY + cg + 8 * (j - LB)] = pr[j];
+        }
 #pragma unroll
         for (int i = Q; i < RI; i++) {
 #pragma unroll
@@ -528,8 +499,11 @@ __global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p
                 if (k < n) {
                     const double* uk = c.UT + k * c.LDU;            // column k of U, contiguous: 16-byte aligned (LDU even)
                     const double2* uk2 = reinterpret_cast<const double2*>(uk);
-                    const bool nz = (y[k] != 0.);
-                    const double z = nz ? y[k] / uk[k] : y[k];
+                    const bool nz = (y[k] != 0.);             // Eigen's triangular solve skips exactly-zero unknowns (no 0/0)
+                    double num = nz ? y[k] : 1., den = nz ? uk[k] : 1.;
+                    opaque(num); opaque(den);
+                    const double zq = num / den;
+                    const double z = nz ? zq : y[k];
                     y[k] = z;
 #pragma unroll
                     for (int r = 0; r < k; r += 2) {

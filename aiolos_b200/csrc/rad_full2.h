@@ -1,0 +1,58 @@
+// Host-visible part of the second-generation full FLD solver (rad_full2.cuh / rad_full2.cu): the shared-memory and HBM
+// geometry both sides agree on, and the launchers.  The kernels live in their own translation unit so that their code
+// generation does not depend on what else the engine's translation unit holds (the 16 k-instruction hydro kernels next to
+// it changed ptxas' register allocation of the LU sweep: 7.4 k instead of 4.4 k instructions, ncu r2c).
+#pragma once
+#include "common.cuh"
+
+namespace aio {
+
+struct Full2Dims {
+    int n, R, RI;
+    int NC;                        // doubles per cell in the coefficient stream (even => 16-byte blocks)
+    int o_D, o_L, o_U, o_B, o_JT, o_TJ, o_TT;
+    int LDXg, XB;                  // row stride (odd => conflict-free lane = row reads) and block size (even) of X_i in HBM
+    int LDU, LDY;
+    int sm_warp;                   // doubles of shared memory per column in k_full_lu
+    int o_col, o_l, o_prow, o_swap, o_UT, o_Y, o_coef, o_bar;      // forward-sweep carve-up
+    int o_ring, o_xs, o_stage;                                      // back-sweep carve-up (aliases the forward one)
+};
+__host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
+    Full2Dims d;
+    d.n = Bout + S;
+    d.RI = (d.n <= 8) ? 2 : (d.n <= 16) ? 4 : 6;
+    d.R = 4 * d.RI;
+    d.o_D = 0; d.o_L = d.R; d.o_U = 2 * d.R; d.o_B = 3 * d.R;
+    d.o_JT = 4 * d.R; d.o_TJ = d.o_JT + Bout * S; d.o_TT = d.o_TJ + S * Bout;
+    d.NC = d.o_TT + S * S; d.NC += d.NC & 1;
+    d.LDXg = (Bout + 1) | 1;
+    d.XB = d.n * d.LDXg; d.XB += d.XB & 1;
+    d.LDU = d.R + 2; d.LDY = d.R;
+    int o = 0;
+    d.o_col = o; o += 32;
+    d.o_l = o; o += d.R;
+    d.o_prow = o; o += 8 * d.RI;
+    d.o_swap = o; o += 8 * d.RI;
+    d.o_UT = o; o += d.R * d.LDU;
+    d.o_Y = o; o += d.R * d.LDY;
+    d.o_coef = o; o += 2 * d.NC;
+    d.o_bar = o; o += 4;
+    const int fwd = o;
+    o = 0;
+    d.o_ring = o; o += 2 * d.XB;
+    d.o_xs = o; o += 32;
+    d.o_stage = o; o += d.n * 8;
+    const int back = o;
+    // the mbarriers keep their place during the back sweep
+    d.sm_warp = (fwd > back + 4) ? fwd : back + 4;
+    if (back > d.o_bar) { d.o_bar = back; }
+    d.sm_warp += d.sm_warp & 1;
+    return d;
+}
+
+constexpr int FULL_ASM_WARPS = 8;
+// cudaFuncSetAttribute for the four kernels; launch of one radiation step on `stream`
+void full2_configure(int RI, size_t smem_lu, size_t smem_asm);
+void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_asm, void* stream);
+
+}  // namespace aio
