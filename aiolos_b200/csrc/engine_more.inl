@@ -57,7 +57,7 @@ void Engine::full_setup() {
         p.ssurf = im->dalloc<double>((size_t)p.ncol * p.Bin);
         im->full_ri = f2.RI;
         im->smem_full2 = (size_t)f2.sm_warp * sizeof(double);
-        im->smem_fasm = (size_t)FULL_ASM_WARPS * 3 * p.S * p.Bout * sizeof(double);
+        im->smem_fasm = (size_t)FULL_ASM_WARPS * (3 * p.S * p.Bout + 2 * p.S) * sizeof(double);
         full2_configure(im->full_ri, im->smem_full2, im->smem_fasm);
         im->full_mode = 2;
     }

@@ -21,7 +21,8 @@
 namespace aio {
 
 // helpers.cpp:227-300
-__device__ inline double planck_integral3(const DevParams& p, double lmin, double lmax, double temperature) {
+// log_spacing = log(p.lT_spacing), hoisted by the caller (the reference evaluates it in place: same value)
+__device__ inline double planck_integral3(const DevParams& p, double lmin, double lmax, double temperature, double log_spacing) {
     if (p.Bout == 1) return 1;
     const double* P = p.planck_matrix;             // [num_plancks][2]: lambda*T, cumulative power
     double lT_min, lT_max;
@@ -34,7 +35,7 @@ __device__ inline double planck_integral3(const DevParams& p, double lmin, doubl
         power_min = P[1] + m * lT_min;
         if (lT_max < P[0]) return 1.;
     } else {
-        const int imin = (int)(log(lT_min / P[0]) / log(p.lT_spacing));
+        const int imin = (int)(log(lT_min / P[0]) / log_spacing);
         m = (P[2 * (imin + 1) + 1] - P[2 * imin + 1]) / (P[2 * (imin + 1)] - P[2 * imin]);
         power_min = P[2 * imin + 1] + m * (lT_min - P[2 * imin]);
     }
@@ -42,11 +43,15 @@ __device__ inline double planck_integral3(const DevParams& p, double lmin, doubl
         power_max = 1.;
         if (lT_min > P[2 * (np - 1)]) return 1;
     } else {
-        const int imax = (int)(log(lT_max / P[0]) / log(p.lT_spacing));
+        const int imax = (int)(log(lT_max / P[0]) / log_spacing);
         m = (P[2 * (imax + 1) + 1] - P[2 * imax + 1]) / (P[2 * (imax + 1)] - P[2 * imax]);
         power_max = P[2 * imax + 1] + m * (lT_max - P[2 * imax]);
     }
     return power_max - power_min;
+}
+
+__device__ inline double planck_integral3(const DevParams& p, double lmin, double lmax, double temperature) {
+    return planck_integral3(p, lmin, lmax, temperature, log(p.lT_spacing));
 }
 
 struct FullDims { int n, LD, LDX, per_warp; };

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) k_full_heat(DevParams p) {
 // ---- block-row coefficients of every cell (radiation.cpp:407-615), parallel over cells -------------------------------------------
 // Per cell, NC doubles:  D[r] diagonal of d_i,  L[r] / U[r] the (diagonal) l_i / u_i entry of J row r,  B[r] right-hand side,
 // JT[b][s] = d_i(J_b, T_s),  TJ[s][b] = d_i(T_s, J_b),  TT[s][s'] off-diagonal T-T couplings (collisional heat exchange).
-__global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p) {
+__global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 3) k_full_asm(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int col = blockIdx.x;
@@ -152,10 +152,13 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
     const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin, Bout = p.Bout;
     const Full2Dims fd = full2_dims(Bout, S);
     const int n = fd.n;
-    // per warp: fac[S][Bout], dterm[S][Bout], rterm[S][Bout]
-    double* facs = sm + (size_t)w * 3 * S * Bout;
+    // per warp: fac[S][Bout], dterm[S][Bout], rterm[S][Bout], and the cell's per-species density and temperature
+    double* facs = sm + (size_t)w * (3 * S * Bout + 2 * S);
     double* dterm = facs + S * Bout;
     double* rterm = dterm + S * Bout;
+    double* rho_s = rterm + S * Bout;
+    double* T_s = rho_s + S;
+    const double log_spacing = log(p.lT_spacing);
     const int CH = (N2 + FULL_ASM_WARPS - 1) / FULL_ASM_WARPS;
     const int i0 = w * CH, i1 = min(N2, i0 + CH);
     const bool isJ = lane < Bout, isT = (lane >= Bout && lane < n);
@@ -183,19 +186,27 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
     }
     for (int i = i0; i < i1; i++) {
         double* cf = p.fcoef + ((size_t)col * N2 + i) * fd.NC;
+        // primitive density and temperature of every species in this cell, once (lanes 0..S-1)
+        if (lane < S && i <= N) {
+            const SpeciesConst sc = p.sp[lane];
+            const double u1 = p.u[idx_u(p, 0, col, lane, i)], u2 = p.u[idx_u(p, 1, col, lane, i)], u3 = p.u[idx_u(p, 2, col, lane, i)];
+            Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+            rho_s[lane] = q.rho;
+            T_s[lane] = p.Tsave ? p.Tsave[idx_s(p, col, lane, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+        }
+        __syncwarp();
         // fac[s][b] = no_rad_trans * kappa_P * sigma T^3 / pi * planck fraction, and the T-row terms built from it
         if (isJ && i <= N) {
             for (int s = 0; s < S; s++) {
-                const SpeciesConst sc = p.sp[s];
-                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
-                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
-                const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
-                const double fac = 1. * p.no_rad_trans * kapv(p, col, s, Bin + lane, i) * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
-                                   planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts);
+                const double cv = p.sp[s].cv;
+                const double Ts = T_s[s];
+                const double kP = kapv(p, col, s, Bin + lane, i);
+                const double fac = 1. * p.no_rad_trans * kP * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
+                                   planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts, log_spacing);
                 facs[s * Bout + lane] = fac;
-                dterm[s * Bout + lane] = 16 * C_PI * fac / sc.cv;
-                rterm[s * Bout + lane] = 12 * C_PI * fac * Ts / sc.cv;
-                cf[fd.o_TJ + s * Bout + lane] = -4 * C_PI * kapv(p, col, s, Bin + lane, i) * p.no_rad_trans / sc.cv;
+                dterm[s * Bout + lane] = 16 * C_PI * fac / cv;
+                rterm[s * Bout + lane] = 12 * C_PI * fac * Ts / cv;
+                cf[fd.o_TJ + s * Bout + lane] = -4 * C_PI * kP * p.no_rad_trans / cv;
             }
         } else if (isJ) {
             for (int s = 0; s < S; s++) cf[fd.o_TJ + s * Bout + lane] = 0.;
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
             if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
             if (i == p.ng - 1 && p.use_planetary_temperature) {      // surface cell radiates at T_planet (radiation.cpp:451-472)
                 const double Tp = cst.T_planet;
-                double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp));
+                double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp), log_spacing);
                 if (Tp < 0) Ssrc *= -1;
                 const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
                 double rhokr = smax(2. * (to_i * to_ip) / (to_i + to_ip), 4. / 3. / dxc);
@@ -249,15 +260,12 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
             for (int s = 0; s < S; s++) {
                 double jt = 0.;
                 if (coupled) {
-                    const SpeciesConst sc = p.sp[s];
-                    const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
-                    Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
-                    const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                    const double rho = rho_s[s], Ts = T_s[s];
                     const double fac = facs[s * Bout + b];
                     const double vj = __ldg(p.vol + i);
-                    d += vj * q.rho * kapv(p, col, s, Bin + b, i) * p.no_rad_trans;
-                    jt = -4 * vj * q.rho * fac;
-                    rhs -= 3 * vj * q.rho * fac * Ts;
+                    d += vj * rho * kapv(p, col, s, Bin + b, i) * p.no_rad_trans;
+                    jt = -4 * vj * rho * fac;
+                    rhs -= 3 * vj * rho * fac * Ts;
                 }
                 cf[fd.o_JT + b * S + s] = jt;
             }
@@ -267,9 +275,7 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
             for (int sj = 0; sj < S; sj++) cf[fd.o_TT + s * S + sj] = 0.;
             if (i <= N) {
                 const SpeciesConst sc = p.sp[s];
-                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
-                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
-                const double Ts = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                const double u1 = rho_s[s], Ts = T_s[s];
                 double d = 1 / dt;
                 rhs = Ts / dt;
                 rhs += (p.dS[idx_s(p, col, s, i)] + 0.) / u1 / sc.cv;
@@ -286,9 +292,7 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 2) k_full_asm(DevParams p
                     double diag_sum = 0, self = 0;
                     for (int sj = 0; sj < S; sj++) {
                         const SpeciesConst cj = p.sp[sj];
-                        const double w1 = p.u[idx_u(p, 0, col, sj, i)], w2 = p.u[idx_u(p, 1, col, sj, i)], w3 = p.u[idx_u(p, 2, col, sj, i)];
-                        Prim3 qj = cons_to_prim(w1, w2, w3, cj.gm1);
-                        const double Tj = p.Tsave ? p.Tsave[idx_s(p, col, sj, i)] : eint_of(qj.p, qj.rho, cj.gm1) / cj.cv;
+                        const double w1 = rho_s[sj], Tj = T_s[sj];
                         double fc = p.fric_mask[s * S + sj] * alpha_pair(p, s, sj, S, sc, cj, u1, w1, w1 / cj.mass, Ts, Tj, tnow);
                         fc *= 3 * C_KB / (sc.cv * (sc.mass + cj.mass));
                         diag_sum += fc;
