@@ -319,7 +319,15 @@ __global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 3) k_full_asm(DevParams p
 template <int RI>
 struct LuCtx {
     static constexpr int R = 4 * RI, LDU = R + 2, LDY = R;      // same numbers as full2_dims(); compile-time here
-    double* colb; double* lb; double* prow; double* swp; double* UT; double* Y;
+    double* colb; double* UT; double* Y;
+    // this lane's windows into the broadcast buffers
+    double* my_col;     // colb + rg            : rows rg + 4 i of the published column
+    double* my_l;       // lb + rg * RI         : multipliers of this lane's rows
+    double* my_l_out;   // lb slot of row `lane` (lane = row during the pivot search)
+    double* my_prow;    // prow + cg * RI       : pivot row entries of this lane's columns
+    double* my_swp;     // swp + cg * RI
+    double* my_UT;      // UT + cg * LDU        : U(k, cg + 8 j) goes to my_UT[8 j LDU + k]
+    double* my_Y;       // Y + cg               : Y(k, cg + 8 j') goes to my_Y[k LDY + 8 j']
     int n, rg, cg, lane;
 };
 
@@ -328,6 +336,7 @@ template <int RI, int Q>
 __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c) {
     constexpr int JK = Q / 2;          // local column block that holds column k
     constexpr int LB = RI / 2;         // column blocks of the LU part; blocks LB.. are the right-hand sides
+    constexpr int LDU = LuCtx<RI>::LDU, LDY = LuCtx<RI>::LDY;
     const int lane = c.lane, rg = c.rg, cg = c.cg;
 #pragma unroll 1
     for (int kk = 0; kk < 4; kk++) {
@@ -337,11 +346,11 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
         // 1. publish column k (live rows only)
         if (cg == cgk) {
 #pragma unroll
-            for (int i = Q; i < RI; i++) c.colb[rg + 4 * i] = a[i][JK];
+            for (int i = Q; i < RI; i++) c.my_col[4 * i] = a[i][JK];
         }
         __syncwarp();
         // 2. pivot search, lane = row: first row holding the largest |a(r,k)|, r >= k  (PartialPivLU)
-        const double v = c.colb[lane < 4 * RI ? lane : 0];
+        const double v = c.colb[lane];
         const bool cand = (lane >= k) && (lane < c.n);
         const double av = fabs(v);
         const unsigned hk = cand ? hi32(av) + 1u : 0u;
@@ -352,57 +361,65 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
         const unsigned votes = __ballot_sync(0xffffffffu, top && (lk == ml));
         const int piv = __ffs(votes) - 1;
         const bool nonzero = !(mh == 1u && ml == 0u);
-        // 3. multipliers; after the row exchange position piv holds the old row k
-        const double pv = c.colb[piv];
-        const double vk = c.colb[k];
+        const bool swap = (piv != k);                     // warp-uniform
+        // 3. multipliers; after the row exchange position piv holds the old row k.
         // Rows k+1 .. n-1 are live.  Zero entries (structural zeros of the blocks are common) and dead lanes must not reach
         // the division: a zero numerator sends the whole warp through the IEEE slow path of the FP64 division (ncu r2b: 22 %
         // of all executed instructions).  0 / pv = 0, so they bypass it.
-        const double mine = (lane == piv) ? vk : v;
+        const double pv = c.colb[piv];
+        double mine = v;
+        if (swap) { const double vk = c.colb[k]; mine = (lane == piv) ? vk : v; }
         const bool live = (lane > k) && (lane < c.n);
         const bool divide = live && nonzero && (mine != 0.);
         double num = divide ? mine : 1., den = divide ? pv : 1.;
         opaque(num); opaque(den);
         const double q = num / den;
         const double l = divide ? q : (live ? mine : 0.);
-        if (lane < 4 * RI) c.lb[(lane & 3) * RI + (lane >> 2)] = l;
+        if (lane < 4 * RI) *c.my_l_out = l;
         // 4. broadcast copy of the pivot row for the update (it becomes row k of U and of the eliminated right-hand sides in 6.)
+        //    5. when rows were exchanged, the old row k (lanes rg == kk, local row Q) moves to position piv
         const int ip = piv >> 2, rgp = piv & 3;
-        if (rg == rgp) {
+        if (!swap) {                    // the usual case: the pivot row is row k itself, local row Q of the lanes rg == kk
+            if (rg == kk) {
 #pragma unroll
-            for (int i = Q; i < RI; i++)
-                if (i == ip) {          // ip is warp-uniform: a branch, the stores read the registers of row i directly
+                for (int j = JK; j < RI; j++) c.my_prow[j] = a[Q][j];
+            }
+            __syncwarp();
+        } else {
+            if (rg == rgp) {
 #pragma unroll
-                    for (int j = JK; j < RI; j++) c.prow[cg * RI + j] = a[i][j];
-                }
-        }
-        // 5. the old row k (lanes rg == kk, local row Q) moves to position piv
-        const bool swap = (piv != k);
-        if (swap && rg == kk) {
+                for (int i = Q; i < RI; i++)
+                    if (i == ip) {      // ip is warp-uniform: a branch, the stores read the registers of row i directly
 #pragma unroll
-            for (int j = JK; j < RI; j++) c.swp[cg * RI + j] = a[Q][j];
-        }
-        __syncwarp();
-        if (swap && rg == rgp) {
+                        for (int j = JK; j < RI; j++) c.my_prow[j] = a[i][j];
+                    }
+            }
+            if (rg == kk) {
 #pragma unroll
-            for (int i = Q; i < RI; i++)
-                if (i == ip) {
+                for (int j = JK; j < RI; j++) c.my_swp[j] = a[Q][j];
+            }
+            __syncwarp();
+            if (rg == rgp) {
 #pragma unroll
-                    for (int j = JK; j < RI; j++) a[i][j] = c.swp[cg * RI + j];
-                }
+                for (int i = Q; i < RI; i++)
+                    if (i == ip) {
+#pragma unroll
+                        for (int j = JK; j < RI; j++) a[i][j] = c.my_swp[j];
+                    }
+            }
         }
         // 6. rank-1 update of the live block; one row group files the pivot row: U transposed (column k of U is read
         //    contiguously by the back substitution), forward-eliminated right-hand sides by row
         double lv[RI], pr[RI];
 #pragma unroll
-        for (int i = Q; i < RI; i++) lv[i] = c.lb[rg * RI + i];
+        for (int i = Q; i < RI; i++) lv[i] = c.my_l[i];
 #pragma unroll
-        for (int j = JK; j < RI; j++) pr[j] = c.prow[cg * RI + j];
+        for (int j = JK; j < RI; j++) pr[j] = c.my_prow[j];
         if (rg == kk) {
 #pragma unroll
-            for (int j = JK; j < LB; j++) c.UT[(cg + 8 * j) * c.LDU + k] = pr[j];
+            for (int j = JK; j < LB; j++) c.my_UT[8 * j * LDU + k] = pr[j];
 #pragma unroll
-            for (int j = LB; j < RI; j++) c.Y[k * c.LDY + cg + 8 * (j - LB)] = pr[j];
+            for (int j = LB; j < RI; j++) c.my_Y[k * LDY + 8 * (j - LB)] = pr[j];
         }
 #pragma unroll
         for (int i = Q; i < RI; i++) {
@@ -420,14 +437,16 @@ __global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p
     const ColState& cst = p.cs[col];
     if (!cst.in_step) return;
     const int N2 = p.N2, S = p.S, Bout = p.Bout;
-    const Full2Dims fd = full2_dims(Bout, S);
+    const Full2Dims fd = full2_dims_ri(Bout, S, RI);
     const int n = fd.n;
     constexpr int R = 4 * RI, LB = RI / 2;
     LuCtx<RI> c;
-    c.colb = sm + fd.o_col; c.lb = sm + fd.o_l; c.prow = sm + fd.o_prow; c.swp = sm + fd.o_swap;
-    c.UT = sm + fd.o_UT; c.Y = sm + fd.o_Y; c.n = n;
-    c.rg = lane >> 3; c.cg = lane & 7; c.lane = lane;
+    c.rg = lane >> 3; c.cg = lane & 7; c.lane = lane; c.n = n;
     const int rg = c.rg, cg = c.cg;
+    c.colb = sm + fd.o_col; c.UT = sm + fd.o_UT; c.Y = sm + fd.o_Y;
+    c.my_col = c.colb + rg; c.my_l = sm + fd.o_l + rg * RI; c.my_l_out = sm + fd.o_l + (lane & 3) * RI + ((lane >> 2) % RI);
+    c.my_prow = sm + fd.o_prow + cg * RI; c.my_swp = sm + fd.o_swap + cg * RI;
+    c.my_UT = c.UT + cg * c.LDU; c.my_Y = c.Y + cg;
     double* coefs = sm + fd.o_coef;
     double* bars = sm + fd.o_bar;                  // [0,1]: coefficient ring, [2,3]: X ring of the back sweep
     const double* cf_g = p.fcoef + (size_t)col * N2 * fd.NC;

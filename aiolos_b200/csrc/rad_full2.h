@@ -17,10 +17,11 @@ struct Full2Dims {
     int o_col, o_l, o_prow, o_swap, o_UT, o_Y, o_coef, o_bar;      // forward-sweep carve-up
     int o_ring, o_xs, o_stage;                                      // back-sweep carve-up (aliases the forward one)
 };
-__host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
+// RI is a function of n; the kernels pass their template parameter so that everything that depends only on RI folds
+__host__ __device__ inline Full2Dims full2_dims_ri(int Bout, int S, int RI) {
     Full2Dims d;
     d.n = Bout + S;
-    d.RI = (d.n <= 8) ? 2 : (d.n <= 16) ? 4 : 6;
+    d.RI = RI;
     d.R = 4 * d.RI;
     d.o_D = 0; d.o_L = d.R; d.o_U = 2 * d.R; d.o_B = 3 * d.R;
     d.o_JT = 4 * d.R; d.o_TJ = d.o_JT + Bout * S; d.o_TT = d.o_TJ + S * Bout;
@@ -48,6 +49,10 @@ __host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
     if (back > d.o_bar) { d.o_bar = back; }
     d.sm_warp += d.sm_warp & 1;
     return d;
+}
+__host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
+    const int n = Bout + S;
+    return full2_dims_ri(Bout, S, (n <= 8) ? 2 : (n <= 16) ? 4 : 6);
 }
 
 constexpr int FULL_ASM_WARPS = 8;
