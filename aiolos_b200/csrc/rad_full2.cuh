@@ -332,25 +332,45 @@ struct LuCtx {
 };
 
 // Elimination steps k = 4Q .. 4Q+3: rows of local index < Q and column blocks < Q/2 are finished (dead registers).
+//
+// The step is latency-bound (ncu r2e: one warp issues an instruction every ~8 cycles, the chain  publish column -> pivot
+// search -> division -> multipliers -> update -> next column  is strictly serial), so the loop is software-pipelined:
+//   * the multipliers are computed speculatively with the diagonal entry as pivot while the pivot search runs (the blocks are
+//     diagonally dominant almost everywhere; a row exchange redoes the division),
+//   * of the rank-1 update of step k only the block column that holds column k+1 is applied at once, so that column k+1 can
+//     be published; the rest of the update is deferred into step k+1, where it fills the latency of that step's pivot
+//     search and division (same basic block: the compiler interleaves the two).
 template <int RI, int Q>
 __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c) {
     constexpr int JK = Q / 2;          // local column block that holds column k
     constexpr int LB = RI / 2;         // column blocks of the LU part; blocks LB.. are the right-hand sides
     constexpr int LDU = LuCtx<RI>::LDU, LDY = LuCtx<RI>::LDY;
     const int lane = c.lane, rg = c.rg, cg = c.cg;
+    if (4 * Q >= c.n) return;
+    // publish column 4Q (live rows only)
+    if (cg == 4 * (Q & 1)) {
+#pragma unroll
+        for (int i = Q; i < RI; i++) c.my_col[4 * i] = a[i][JK];
+    }
+    bool deferred = false;
 #pragma unroll 1
     for (int kk = 0; kk < 4; kk++) {
         const int k = 4 * Q + kk;
         if (k >= c.n) break;
-        const int cgk = 4 * (Q & 1) + kk;
-        // 1. publish column k (live rows only)
-        if (cg == cgk) {
-#pragma unroll
-            for (int i = Q; i < RI; i++) c.my_col[4 * i] = a[i][JK];
-        }
         __syncwarp();
-        // 2. pivot search, lane = row: first row holding the largest |a(r,k)|, r >= k  (PartialPivLU)
+        // 1. column k as published; multipliers and rest of the previous update from the broadcast buffers of step k-1
         const double v = c.colb[lane];
+        const double vk = c.colb[k];
+        const bool live = (lane > k) && (lane < c.n);
+        // speculative multipliers l = a(r,k) / a(k,k).  Zero entries (structural zeros of the blocks are common) and dead lanes
+        // must not reach the division: a zero numerator sends the whole warp through the IEEE slow path of the FP64 division
+        // (ncu r2b: 22 % of all executed instructions).  0 / pv = 0, so they bypass it.
+        const bool dspec = live && (v != 0.) && (vk != 0.);
+        double num = dspec ? v : 1., den = dspec ? vk : 1.;
+        opaque(num); opaque(den);
+        const double qspec = num / den;
+        double l = dspec ? qspec : (live ? v : 0.);
+        // 2. pivot search, lane = row: first row holding the largest |a(r,k)|, r >= k  (PartialPivLU)
         const bool cand = (lane >= k) && (lane < c.n);
         const double av = fabs(v);
         const unsigned hk = cand ? hi32(av) + 1u : 0u;
@@ -360,29 +380,44 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
         const unsigned ml = warp_umax(lk);
         const unsigned votes = __ballot_sync(0xffffffffu, top && (lk == ml));
         const int piv = __ffs(votes) - 1;
-        const bool nonzero = !(mh == 1u && ml == 0u);
         const bool swap = (piv != k);                     // warp-uniform
-        // 3. multipliers; after the row exchange position piv holds the old row k.
-        // Rows k+1 .. n-1 are live.  Zero entries (structural zeros of the blocks are common) and dead lanes must not reach
-        // the division: a zero numerator sends the whole warp through the IEEE slow path of the FP64 division (ncu r2b: 22 %
-        // of all executed instructions).  0 / pv = 0, so they bypass it.
-        const double pv = c.colb[piv];
-        double mine = v;
-        if (swap) { const double vk = c.colb[k]; mine = (lane == piv) ? vk : v; }
-        const bool live = (lane > k) && (lane < c.n);
-        const bool divide = live && nonzero && (mine != 0.);
-        double num = divide ? mine : 1., den = divide ? pv : 1.;
-        opaque(num); opaque(den);
-        const double q = num / den;
-        const double l = divide ? q : (live ? mine : 0.);
+        // 3. the deferred part of the update of step k-1 (block columns right of the one that holds column k)
+        if (deferred) {
+            double lvp[RI], prp[RI];
+#pragma unroll
+            for (int i = Q; i < RI; i++) lvp[i] = c.my_l[i];
+#pragma unroll
+            for (int j = JK + 1; j < RI; j++) prp[j] = c.my_prow[j];
+#pragma unroll
+            for (int i = Q; i < RI; i++) {
+#pragma unroll
+                for (int j = JK + 1; j < RI; j++) a[i][j] = d_fnma(lvp[i], prp[j], a[i][j]);
+            }
+        }
+        // 4. a row exchange invalidates the speculation: position piv now holds the old row k, the pivot is a(piv,k) != 0
+        if (swap) {
+            const double pv = c.colb[piv];
+            const double mine = (lane == piv) ? vk : v;
+            const bool divide = live && (mine != 0.);
+            double num2 = divide ? mine : 1., den2 = divide ? pv : 1.;
+            opaque(num2); opaque(den2);
+            const double q2 = num2 / den2;
+            l = divide ? q2 : (live ? mine : 0.);
+        }
+        __syncwarp();                   // every lane has read the buffers of step k-1
         if (lane < 4 * RI) *c.my_l_out = l;
-        // 4. broadcast copy of the pivot row for the update (it becomes row k of U and of the eliminated right-hand sides in 6.)
-        //    5. when rows were exchanged, the old row k (lanes rg == kk, local row Q) moves to position piv
+        // 5. the pivot row: broadcast copy for the update; it is row k of U (stored transposed: the back substitution reads
+        //    column k of U contiguously) and of the forward-eliminated right-hand sides.  After an exchange the old row k
+        //    (lanes rg == kk, local row Q) moves to position piv.
         const int ip = piv >> 2, rgp = piv & 3;
         if (!swap) {                    // the usual case: the pivot row is row k itself, local row Q of the lanes rg == kk
             if (rg == kk) {
 #pragma unroll
                 for (int j = JK; j < RI; j++) c.my_prow[j] = a[Q][j];
+#pragma unroll
+                for (int j = JK; j < LB; j++) c.my_UT[8 * j * LDU + k] = a[Q][j];
+#pragma unroll
+                for (int j = LB; j < RI; j++) c.my_Y[k * LDY + 8 * (j - LB)] = a[Q][j];
             }
             __syncwarp();
         } else {
@@ -392,6 +427,10 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
                     if (i == ip) {      // ip is warp-uniform: a branch, the stores read the registers of row i directly
 #pragma unroll
                         for (int j = JK; j < RI; j++) c.my_prow[j] = a[i][j];
+#pragma unroll
+                        for (int j = JK; j < LB; j++) c.my_UT[8 * j * LDU + k] = a[i][j];
+#pragma unroll
+                        for (int j = LB; j < RI; j++) c.my_Y[k * LDY + 8 * (j - LB)] = a[i][j];
                     }
             }
             if (rg == kk) {
@@ -408,25 +447,32 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
                     }
             }
         }
-        // 6. rank-1 update of the live block; one row group files the pivot row: U transposed (column k of U is read
-        //    contiguously by the back substitution), forward-eliminated right-hand sides by row
-        double lv[RI], pr[RI];
+        // 6. update the block column that holds column k+1 and publish that column; the rest waits for step k+1
+        {
+            const double pj = c.my_prow[JK];
 #pragma unroll
-        for (int i = Q; i < RI; i++) lv[i] = c.my_l[i];
-#pragma unroll
-        for (int j = JK; j < RI; j++) pr[j] = c.my_prow[j];
-        if (rg == kk) {
-#pragma unroll
-            for (int j = JK; j < LB; j++) c.my_UT[8 * j * LDU + k] = pr[j];
-#pragma unroll
-            for (int j = LB; j < RI; j++) c.my_Y[k * LDY + 8 * (j - LB)] = pr[j];
+            for (int i = Q; i < RI; i++) a[i][JK] = d_fnma(c.my_l[i], pj, a[i][JK]);
         }
+        deferred = true;
+        if (kk < 3 && k + 1 < c.n && cg == 4 * (Q & 1) + kk + 1) {
+#pragma unroll
+            for (int i = Q; i < RI; i++) c.my_col[4 * i] = a[i][JK];
+        }
+    }
+    // the deferred part of the phase's last step
+    if (deferred) {
+        double lvp[RI], prp[RI];
+#pragma unroll
+        for (int i = Q; i < RI; i++) lvp[i] = c.my_l[i];
+#pragma unroll
+        for (int j = JK + 1; j < RI; j++) prp[j] = c.my_prow[j];
 #pragma unroll
         for (int i = Q; i < RI; i++) {
 #pragma unroll
-            for (int j = JK; j < RI; j++) a[i][j] = d_fnma(lv[i], pr[j], a[i][j]);
+            for (int j = JK + 1; j < RI; j++) a[i][j] = d_fnma(lvp[i], prp[j], a[i][j]);
         }
     }
+    __syncwarp();
 }
 
 template <int RI>
