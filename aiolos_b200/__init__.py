@@ -47,6 +47,7 @@ class _Override(C.Structure):
 
 _SYMBOLS = {
     "aio_device_count": (C.c_int, []),
+    "aio_device_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "aio_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_Override), C.c_int, C.c_int,
                              C.POINTER(C.c_void_p)]),
     "aio_create_from_dump": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_Override), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -70,6 +71,7 @@ _SYMBOLS = {
     "aio_write_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "aio_write_monitor": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "aio_kernel_launches": (C.c_longlong, [C.c_void_p]),
+    "aio_kernel_name": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "aio_total_steps": (C.c_longlong, [C.c_void_p]),
     "aio_last_error": (C.c_char_p, []),
     "aio_version": (C.c_char_p, []),
@@ -104,6 +106,16 @@ def _mk_overrides(overrides: Optional[Iterable[Tuple[int, str, str]]]):
         keep += [k, v]
         arr[i].column = int(col); arr[i].key = k; arr[i].value = v
     return arr, len(items), keep
+
+
+def device_peaks(device: int = 0, lib: Optional[str] = None, copy: bool = True):
+    """Measured FP64 FMA rate (TFLOP/s) and copy bandwidth (GB/s) of one GPU: the roofline denominators bench.py uses."""
+    L = load_library(lib)
+    f, b = C.c_double(0.0), C.c_double(0.0)
+    rc = L.aio_device_peaks(device, C.byref(f), C.byref(b) if copy else None)
+    if rc != 0:
+        raise AiolosError(rc, L.aio_last_error().decode())
+    return {"fp64_tflops": f.value, "copy_gbs": b.value if copy else None}
 
 
 class Ensemble:
@@ -183,6 +195,13 @@ class Ensemble:
         out = np.zeros(3)
         self._ck(self._lib.aio_kernel_times(self._h, int(steps), out.ctypes.data))
         return {"hydro": out[0], "friction": out[1], "radiation": out[2]}
+
+    def kernel_name(self, slot) -> str:
+        """Kernel(s) behind one slot of kernel_times ("hydro"/"step" = 0, "friction" = 1, "radiation" = 2)."""
+        i = {"hydro": 0, "step": 0, "friction": 1, "radiation": 2}.get(slot, slot)
+        buf = C.create_string_buffer(256)
+        self._ck(self._lib.aio_kernel_name(self._h, int(i), buf, 256))
+        return buf.value.decode()
 
     def set_option(self, key: str, value: str):
         self._ck(self._lib.aio_set_option(self._h, key.encode(), value.encode()))

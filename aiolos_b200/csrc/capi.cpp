@@ -4,6 +4,7 @@
 #include "hooks.h"
 #include "cuda_compat.h"
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -13,6 +14,8 @@ struct aio_ensemble {
     std::vector<aio::Problem> problems;      // host-side description of every column (kept for the writers)
     std::vector<std::vector<double>> monitor_prev;   // previous_monitor_J / _T per column (io.cpp:1048-1054)
 };
+
+namespace aio { void measure_device_peaks(int device, double* fp64_tflops, double* copy_gbs); }   // peaks.cu
 
 namespace {
 thread_local std::string g_err;
@@ -79,6 +82,15 @@ int aio_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+int aio_device_peaks(int device, double* fp64_tflops, double* copy_gbs) {
+#ifdef AIO_EMU_BUILD
+    (void)device; (void)fp64_tflops; (void)copy_gbs;
+    return fail(AIO_ERR_CUDA, "aio_device_peaks: CUDA device required (emulator build)");
+#else
+    return guarded([&]() { aio::measure_device_peaks(device, fp64_tflops, copy_gbs); return AIO_OK; });
+#endif
 }
 
 int aio_create(const char* dir, const char* par, const char* spc, int ncols, const aio_override* ov, int n_ov, int device,
@@ -232,6 +244,14 @@ int aio_write_monitor(aio_ensemble* e, int column, const char* outdir, int trunc
 }
 
 long long aio_kernel_launches(aio_ensemble* e) { return e ? e->eng->kernel_launches() : 0; }
+int aio_kernel_name(aio_ensemble* e, int slot, char* dst, int capacity) {
+    if (!e || !dst || capacity < 1) return fail(AIO_ERR_ARG, "aio_kernel_name: bad argument");
+    return guarded([&]() {
+        const std::string s = e->eng->kernel_name(slot);
+        snprintf(dst, (size_t)capacity, "%s", s.c_str());
+        return AIO_OK;
+    });
+}
 long long aio_total_steps(aio_ensemble* e) {
     if (!e) return 0;
     try { return e->eng->total_steps(); } catch (...) { return -1; }

@@ -2,6 +2,7 @@
 #pragma once
 #include "problem.h"
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace aio {
@@ -32,6 +33,7 @@ public:
     void sync();
     int ncol() const; int num_cells() const; int num_species() const; int num_bands_out() const; int num_bands_in() const;
     long long kernel_launches() const;
+    std::string kernel_name(int slot) const;                    // what aio_kernel_times slot 0/1/2 launches
     void* stream() const;
     const Problem& problem0() const { return prob0; }
 

@@ -78,4 +78,36 @@ void Engine::launch_full() {
     else AIO_LAUNCH(k_rad_full<32>, grid, im->nt_full, im->smem_full, im->stream, p);
 }
 
+// Name of the kernel(s) the engine launches for one slot of aio_kernel_times (0 hydro / fused step, 1 friction, 2 radiation),
+// from the same switches launch_step() dispatches on.
+std::string Engine::kernel_name(int slot) const {
+    const DevParams& p = im->p;
+    const std::string cpt = std::to_string(im->CPT);
+    if (slot == 0) {
+        if (im->fused && im->v2) return "k_step1<" + cpt + "," + std::to_string(im->NT) + "," + std::to_string(im->step1_ctas) + ">";
+        if (im->v2) return "k_hydro2<" + cpt + ">";
+        return "k_hydro<" + cpt + (im->NT > 256 ? "," + std::to_string(im->NT) : "") + ">";
+    }
+    if (slot == 1) {
+        if (!im->has_friction) return "";
+        const int S = p.S;
+        return "k_friction<" + std::to_string(S <= 2 ? 2 : S <= 3 ? 3 : S <= 4 ? 4 : S <= 6 ? 6 : S <= 8 ? 8 : 16) + ">";
+    }
+    if (slot == 2) {
+        std::string pre = p.kap_cell ? "k_opacity + " : "";
+        if (p.use_rad_fluxes == 1) {
+            if (im->full_mode == 2) return pre + "k_full_heat + k_full_asm + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
+            return pre + "k_rad_full<" + std::to_string(im->full_mode == 0 ? 0 : (p.Bout + p.S + 7) / 8 * 8) + ">";
+        }
+        if (p.use_rad_fluxes == 2) {
+            if (im->fused && im->v2) return "";
+            if (im->v2 && p.S == 1 && !p.Tsave && !p.kap_cell) return "k_rad3<" + cpt + ">";
+            if (im->v2 && !(p.use_collisional_heating && p.S > 1) && !p.kap_cell) return "k_rad2<" + cpt + ">";
+            return pre + "k_rad_simple<" + cpt + ">";
+        }
+        return "";
+    }
+    throw std::invalid_argument("kernel_name: slot outside 0..2");
+}
+
 }  // namespace aio

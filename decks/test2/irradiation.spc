@@ -1,0 +1,6 @@
+#
+# This file contains a template for a list of species in the form of a table
+# every row is one species and starts with a * and a number. Row contents are listed below
+# 
+# 1:Number 2:Name 3:mass in amu 4:dof               5:adiabatic index initially 6:relative amount 7:initial density excess 8: is_dust_like 9:opacity.opa 10:opa file length
+@ 0        S1     1.0         3.                   1.4                         1.0                 -0.9999                      0              highenergy3.opa  

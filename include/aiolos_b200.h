@@ -58,6 +58,10 @@ typedef struct aio_override {
 #define AIO_F_J0 16         /* c_Sim::Jrad_FLD(j, b): field = AIO_F_J0 + b */
 
 int aio_device_count(void);
+/* Measured roofline denominators of one device (no reference counterpart; bench.py reports against them): the FP64 FMA
+ * rate of the SMs in TFLOP/s (2 flop per DFMA) and the device-to-device copy bandwidth in GB/s (read + write bytes).
+ * Either pointer may be NULL. */
+int aio_device_peaks(int device, double* fp64_tflops, double* copy_gbs);
 
 int aio_create(const char* dir, const char* par, const char* spc, int ncols, const aio_override* ov, int n_ov,
                int device, aio_ensemble** out);
@@ -108,6 +112,9 @@ int aio_write_outputs(aio_ensemble* e, int column, int index, const char* outdir
 int aio_write_monitor(aio_ensemble* e, int column, const char* outdir, int truncate);
 
 long long aio_kernel_launches(aio_ensemble* e);
+/* Name(s) of the kernel(s) behind slot 0/1/2 (hydro or fused step, friction, radiation) of aio_kernel_times for this
+ * ensemble, e.g. "k_step1<4,256,3>": what bench.py names in its roofline records. */
+int aio_kernel_name(aio_ensemble* e, int slot, char* dst, int capacity);
 long long aio_total_steps(aio_ensemble* e);      /* sum over columns of completed steps */
 const char* aio_last_error(void);
 const char* aio_version(void);

@@ -123,11 +123,11 @@ def test_crashed_column_freezes_others_continue(lib):
 
 
 def test_from_files_matches_reference(lib, monkeypatch):
-    """The drop-in entry point on the GPU: configs[3] built from its own .par/.spc/.opa (oracle/decks holds the unmodified
+    """The drop-in entry point on the GPU: configs[3] built from its own .par/.spc/.opa (decks/ holds the unmodified
     inputs), 100 steps, against the reference's state; and the front end's arrays against the reference constructor's."""
     from aiodump import read_dump
     from conftest import ROOT
-    monkeypatch.chdir(os.path.join(ROOT, "oracle", "decks"))
+    monkeypatch.chdir(os.path.join(ROOT, "decks"))
     ens = A.Ensemble.from_files("runs_mdot_vs_euv_plot/", "dynamic3_euv1e3_C_1s2b_rerun.par", "", ncols=4, lib=lib)
     init = read_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_init.bin"))
     for name in ("x_i12", "vol", "phi", "planck_matrix", "solar_heating_final", "Jrad_FLD", "s0.u1", "s0.u3", "s0.opacity_avg_solar"):
@@ -166,7 +166,7 @@ def plugin_lib():
 
 def _dusty_wind(plugin_lib, monkeypatch, ncols=1, overrides=None, par="dusty_wind_1k.par"):
     from conftest import ROOT
-    monkeypatch.chdir(os.path.join(ROOT, "oracle", "decks"))                  # inputdata/smalldust.opa, relative to the CWD
+    monkeypatch.chdir(os.path.join(ROOT, "decks"))                  # inputdata/smalldust.opa, relative to the CWD
     return A.Ensemble.from_files(os.path.join(GOLDEN, "decks") + "/", par, "silicate.spc", ncols=ncols,
                                  overrides=overrides, lib=plugin_lib)
 

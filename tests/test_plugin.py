@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "aiolos_b200", "plugin"))
 from prepare_problem import transform  # noqa: E402
 
 DECK_DIR = os.path.join(GOLDEN, "decks") + "/"
-RUN_DIR = os.path.join(ROOT, "oracle", "decks")          # holds inputdata/smalldust.opa (opened relative to the CWD)
+RUN_DIR = os.path.join(ROOT, "decks")          # holds inputdata/smalldust.opa (opened relative to the CWD)
 
 
 def test_prepare_problem_transform():

@@ -31,7 +31,7 @@ def run_twins(uvs, tmax, workdir):
     procs, dirs = [], []
     for i, uv in enumerate(uvs):
         d = os.path.join(workdir, f"p{i}")
-        shutil.copytree(os.path.join(ROOT, "oracle", "decks"), d)
+        shutil.copytree(os.path.join(ROOT, "decks"), d)
         par = os.path.join(d, bench.DECK_DIR, bench.DECK_PAR)
         txt = open(par).read().splitlines()
         txt = [("PARI_UVSTAR             %.17g" % uv) if ln.startswith("PARI_UVSTAR") else ln for ln in txt]
@@ -70,7 +70,7 @@ def main():
         ov.append((-1, "PARI_TIME_TMAX", repr(a.tmax)))
     cwd = os.getcwd()
     lib = os.path.abspath(a.lib) if a.lib else None
-    os.chdir(os.path.join(ROOT, "oracle", "decks"))      # opacity files are opened relative to the CWD (io.cpp:143)
+    os.chdir(os.path.join(ROOT, "decks"))      # opacity files are opened relative to the CWD (io.cpp:143)
     try:
         ens = A.Ensemble.from_files(bench.DECK_DIR, bench.DECK_PAR, "", ncols=n, overrides=ov, lib=lib)
     finally:
