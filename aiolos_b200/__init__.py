@@ -48,6 +48,7 @@ class _Override(C.Structure):
 _SYMBOLS = {
     "aio_device_count": (C.c_int, []),
     "aio_device_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "aio_selftest_block_thomas": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "aio_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_Override), C.c_int, C.c_int,
                              C.POINTER(C.c_void_p)]),
     "aio_create_from_dump": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_Override), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -116,6 +117,19 @@ def device_peaks(device: int = 0, lib: Optional[str] = None, copy: bool = True):
     if rc != 0:
         raise AiolosError(rc, L.aio_last_error().decode())
     return {"fp64_tflops": f.value, "copy_gbs": b.value if copy else None}
+
+
+def block_thomas(coef: np.ndarray, bands_out: int, num_species: int, lib: Optional[str] = None) -> np.ndarray:
+    """Run the product's block-Thomas sweep (full FLD solver) on caller-supplied block rows; see aio_selftest_block_thomas.
+    coef: [ncols][cells][NC]; returns x [ncols][cells][n]."""
+    L = load_library(lib)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    ncols, cells, _ = coef.shape
+    x = np.zeros((ncols, cells, bands_out + num_species))
+    rc = L.aio_selftest_block_thomas(ncols, cells, bands_out, num_species, coef.ctypes.data, x.ctypes.data)
+    if rc != 0:
+        raise AiolosError(rc, L.aio_last_error().decode())
+    return x
 
 
 class Ensemble:

@@ -15,6 +15,7 @@ struct aio_ensemble {
     std::vector<std::vector<double>> monitor_prev;   // previous_monitor_J / _T per column (io.cpp:1048-1054)
 };
 
+namespace aio { void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, double* x); }   // rad_full2.cu
 namespace aio { void measure_device_peaks(int device, double* fp64_tflops, double* copy_gbs); }   // peaks.cu
 
 namespace {
@@ -82,6 +83,11 @@ int aio_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+int aio_selftest_block_thomas(int ncols, int num_cells2, int bands_out, int num_species, const double* coef, double* x) {
+    if (!coef || !x) return fail(AIO_ERR_ARG, "aio_selftest_block_thomas: null pointer");
+    return guarded([&]() { aio::full2_selftest(ncols, num_cells2, bands_out, num_species, coef, x); return AIO_OK; });
 }
 
 int aio_device_peaks(int device, double* fp64_tflops, double* copy_gbs) {

@@ -60,4 +60,6 @@ constexpr int FULL_ASM_WARPS = 8;
 void full2_configure(int RI, size_t smem_lu, size_t smem_asm);
 void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_asm, void* stream);
 
+void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, double* x);
+
 }  // namespace aio

@@ -63,6 +63,13 @@ int aio_device_count(void);
  * Either pointer may be NULL. */
 int aio_device_peaks(int device, double* fp64_tflops, double* copy_gbs);
 
+/* Kernel-level known-answer hook for the coupled J_b / T_s block-tridiagonal solve (block_tridiag_solve.h:57-130): runs the
+ * product's block-Thomas sweep on caller-supplied block rows.  coef: [ncols][num_cells2][NC] doubles, per cell
+ *   D[R] L[R] U[R] B[R] JT[bands_out][num_species] TJ[num_species][bands_out] TT[num_species][num_species] (+1 pad if odd)
+ * with R = 8 / 16 / 24 >= n = bands_out + num_species (D: diagonal of d_i; L, U: the diagonal l_i / u_i entries of the J
+ * rows; B: right-hand side; JT / TJ / TT: the J-T, T-J and off-diagonal T-T entries of d_i).  x: [ncols][num_cells2][n]. */
+int aio_selftest_block_thomas(int ncols, int num_cells2, int bands_out, int num_species, const double* coef, double* x);
+
 int aio_create(const char* dir, const char* par, const char* spc, int ncols, const aio_override* ov, int n_ov,
                int device, aio_ensemble** out);
 int aio_create_from_dump(const char* init_dump_path, int ncols, const aio_override* ov, int n_ov, int device,

@@ -9,6 +9,7 @@ namespace emu {
 
 uint3_emu tIdx, bIdx, bDim, gDim;
 void* dyn_smem = nullptr;
+size_t dyn_smem_bytes = 0;
 double xd[1024];
 int xi[1024];
 
@@ -50,6 +51,7 @@ void run_grid(void (*thunk)(void*), void* args, dim3 grid, dim3 block, size_t sm
         for (size_t k = old; k < fibers.size(); k++) fibers[k].stack = (char*)malloc(STACK);
     }
     std::vector<unsigned char> sm(smem + 16);
+    dyn_smem_bytes = smem;
     for (unsigned b = 0; b < grid.x; b++) {
         bIdx = {b, 0, 0};
         memset(sm.data(), 0xff, sm.size());              // all-ones doubles are NaNs

@@ -36,6 +36,7 @@ struct uint3_emu { unsigned x, y, z; };
 namespace emu {
 extern uint3_emu tIdx, bIdx, bDim, gDim;
 extern void* dyn_smem;
+extern size_t dyn_smem_bytes;           // size of the current launch's dynamic shared memory (bounds checks)
 void sync_block();                       // __syncthreads
 void sync_warp();                        // rendezvous of the live fibers of the calling warp
 extern double xd[1024];                  // exchange slots
