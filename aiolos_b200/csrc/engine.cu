@@ -35,7 +35,7 @@ struct Engine::Impl {
     // full FLD: 2 = register-tiled LU, four kernels (rad_full2.cuh; default when n <= 24); 0 = first-generation shared-memory
     // LU, one kernel (rad_full.cuh; option full_lu=smem, and n > 24); 1 = its shuffle-based register variant (full_lu=reg)
     int full_mode = 0;
-    bool full2_ok = false; size_t smem_full2 = 0, smem_fasm = 0; int full_ri = 0;
+    bool full2_ok = false; size_t smem_full2 = 0; int full_ri = 0;
     bool fused = false;             // single-species persistent step kernel (k_step1)
     int step1_ctas = 3;             // resident CTAs per SM the fused kernel is compiled for (3: 80 registers, 2: 128)
     int steps_per_launch = 16;

@@ -57,15 +57,14 @@ void Engine::full_setup() {
         p.ssurf = im->dalloc<double>((size_t)p.ncol * p.Bin);
         im->full_ri = f2.RI;
         im->smem_full2 = (size_t)f2.sm_warp * sizeof(double);
-        im->smem_fasm = (size_t)FULL_ASM_WARPS * (3 * p.S * p.Bout + 2 * p.S) * sizeof(double);
-        full2_configure(im->full_ri, im->smem_full2, im->smem_fasm);
+        full2_configure(im->full_ri, im->smem_full2);
         im->full_mode = 2;
     }
 }
 void Engine::launch_full() {
     DevParams& p = im->p;
     if (im->full_mode == 2) {
-        full2_launch(p, im->full_ri, im->smem_full2, im->smem_fasm, (void*)im->stream);
+        full2_launch(p, im->full_ri, im->smem_full2, (void*)im->stream);
         im->launches += 3;
         return;
     }
@@ -96,7 +95,7 @@ std::string Engine::kernel_name(int slot) const {
     if (slot == 2) {
         std::string pre = p.kap_cell ? "k_opacity + " : "";
         if (p.use_rad_fluxes == 1) {
-            if (im->full_mode == 2) return pre + "k_full_heat + k_full_asm + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
+            if (im->full_mode == 2) return pre + "k_full_heat + k_full_asm2 + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
             return pre + "k_rad_full<" + std::to_string(im->full_mode == 0 ? 0 : (p.Bout + p.S + 7) / 8 * 8) + ">";
         }
         if (p.use_rad_fluxes == 2) {

@@ -7,17 +7,22 @@
 
 namespace aio {
 
-void full2_configure(int RI, size_t smem_lu, size_t smem_asm) {
+void full2_configure(int RI, size_t smem_lu) {
     if (RI == 2) CK(cudaFuncSetAttribute(k_full_lu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
     else if (RI == 4) CK(cudaFuncSetAttribute(k_full_lu<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
     else CK(cudaFuncSetAttribute(k_full_lu<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
-    CK(cudaFuncSetAttribute(k_full_asm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_asm));
 }
 
-void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_asm, void* stream_) {
+void full2_launch(const DevParams& p, int RI, size_t smem_lu, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AIO_LAUNCH(k_full_heat, (p.ncol + 3) / 4, 128, 0, stream, p);
-    AIO_LAUNCH(k_full_asm, p.ncol, 32 * FULL_ASM_WARPS, smem_asm, stream, p);
+    {
+        const unsigned grid = (unsigned)(((long long)p.ncol * p.N2 + 127) / 128);
+        if (p.S <= 1) AIO_LAUNCH(k_full_asm2<1>, grid, 128, 0, stream, p);
+        else if (p.S <= 2) AIO_LAUNCH(k_full_asm2<2>, grid, 128, 0, stream, p);
+        else if (p.S <= 4) AIO_LAUNCH(k_full_asm2<4>, grid, 128, 0, stream, p);
+        else AIO_LAUNCH(k_full_asm2<16>, grid, 128, 0, stream, p);
+    }
     if (RI == 2) AIO_LAUNCH(k_full_lu<2>, p.ncol, 32, smem_lu, stream, p);
     else if (RI == 4) AIO_LAUNCH(k_full_lu<4>, p.ncol, 32, smem_lu, stream, p);
     else AIO_LAUNCH(k_full_lu<6>, p.ncol, 32, smem_lu, stream, p);
@@ -25,8 +30,7 @@ void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_asm, v
 }
 
 // Block-Thomas sweep on caller-supplied block rows (aio_selftest_block_thomas): `coef` holds, per column and cell, the
-// coefficient stream k_full_asm would have written (layout of full2_dims: D[R] L[R] U[R] B[R] JT[Bout][S] TJ[S][Bout]
-// TT[S][S]); x receives the solution [ncols][N2][n] (J rows, then T rows).
+// coefficient stream k_full_asm would have written (band and species records, see Full2Dims in rad_full2.h); x receives the solution [ncols][N2][n] (J rows, then T rows).
 void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, double* x) {
     if (ncols < 1 || N2 < 1 || Bout < 1 || S < 1 || Bout + S > 24 || Bout > MAXB || S > MAXS) throw std::invalid_argument("block_thomas: sizes out of range");
     const Full2Dims fd = full2_dims(Bout, S);
@@ -45,7 +49,7 @@ void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, doub
         CK(cudaMemcpy(p.cs, cs.data(), cs.size() * sizeof(ColState), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p.fcoef, coef, n_coef * 8, cudaMemcpyHostToDevice));
         const size_t smem_lu = (size_t)fd.sm_warp * sizeof(double);
-        full2_configure(fd.RI, smem_lu, 0);
+        full2_configure(fd.RI, smem_lu);
         cudaStream_t stream = nullptr;
         if (fd.RI == 2) AIO_LAUNCH(k_full_lu<2>, ncols, 32, smem_lu, stream, p);
         else if (fd.RI == 4) AIO_LAUNCH(k_full_lu<4>, ncols, 32, smem_lu, stream, p);

@@ -139,180 +139,180 @@ __global__ void __launch_bounds__(128) k_full_heat(DevParams p) {
     if (lane < S) p.dS[idx_s(p, col, lane, 0)] = 0.;
 }
 
-// ---- block-row coefficients of every cell (radiation.cpp:407-615), parallel over cells -------------------------------------------
-// Per cell, NC doubles:  D[r] diagonal of d_i,  L[r] / U[r] the (diagonal) l_i / u_i entry of J row r,  B[r] right-hand side,
-// JT[b][s] = d_i(J_b, T_s),  TJ[s][b] = d_i(T_s, J_b),  TT[s][s'] off-diagonal T-T couplings (collisional heat exchange).
-__global__ void __launch_bounds__(32 * FULL_ASM_WARPS, 3) k_full_asm(DevParams p) {
-    AIO_DYN_SMEM(double, sm);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x;
+// one record of the coefficient stream: `len` doubles (a multiple of 4) as 16-byte stores, i.e. whole 32-byte sectors
+template <int NMAX>
+__device__ __forceinline__ void store_record(double* dst, const double (&rec)[NMAX], int len) {
+#pragma unroll
+    for (int k = 0; k < NMAX; k += 2)
+        if (k < len) *reinterpret_cast<double2*>(dst + k) = make_double2(rec[k], rec[k + 1]);
+}
+
+// ---- block-row coefficients of every cell (radiation.cpp:407-615), one THREAD per cell -- flux limiter, Planck fractions, matter
+// coupling: nothing here depends on the solve.  (The first version ran one lane per band: 22 of 32 lanes busy, the T rows summed
+// by a single lane while its warp waited, 1.7 k warp instructions per cell and 2.9 ms at 4096 columns of configs[2], ncu r2l.)
+// With lane = cell the state loads are coalesced, every lane is busy, the band loop runs inside the thread, so the T-row sums
+// accumulate in registers in the reference's band order, and no shared memory or warp barrier is needed.  The coefficients
+// leave as band / species records (Full2Dims): whole 32-byte sectors per store, no partial-sector fills in L2.
+template <int SMAX>
+__global__ void __launch_bounds__(128) k_full_asm2(DevParams p) {
+    const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin, Bout = p.Bout;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // (column, cell) flattened: no idle tail lanes
+    if (gid >= (long long)p.ncol * N2) return;
+    const int col = (int)(gid / N2), i = (int)(gid - (long long)col * N2);
     const ColState& cst = p.cs[col];
     if (!cst.in_step) return;
     const double dt = cst.dt, tnow = cst.t;
-    const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin, Bout = p.Bout;
     const Full2Dims fd = full2_dims(Bout, S);
     const int n = fd.n;
-    // per warp: fac[S][Bout], dterm[S][Bout], rterm[S][Bout], and the cell's per-species density and temperature
-    double* facs = sm + (size_t)w * (3 * S * Bout + 2 * S);
-    double* dterm = facs + S * Bout;
-    double* rterm = dterm + S * Bout;
-    double* rho_s = rterm + S * Bout;
-    double* T_s = rho_s + S;
+    double* cf = p.fcoef + ((size_t)col * N2 + i) * fd.NC;
     const double log_spacing = log(p.lT_spacing);
-    const int CH = (N2 + FULL_ASM_WARPS - 1) / FULL_ASM_WARPS;
-    const int i0 = w * CH, i1 = min(N2, i0 + CH);
-    const bool isJ = lane < Bout, isT = (lane >= Bout && lane < n);
-    const int sT = lane - Bout;
-    auto total_opacity = [&](int j, int b) -> double {
-        if (j < 1 || j > N + 1) return 0.;
-        double tot = 0;
-        for (int s = 0; s < S; s++) tot = fmax(kapv(p, col, s, Bin + Bout + b, j) * p.u[idx_u(p, 0, col, s, j)], tot);
-        return tot;
-    };
-    auto Jold = [&](int j, int b) -> double { return (j >= 0 && j < N2) ? p.J[idx_J(p, col, b, j)] : 0.; };
-    auto Dcoef = [&](int i, int b, double Jc, double Jn, double toi, double toip) -> double {
-        const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+    // densities of the cell and its neighbours (total opacity), primitive temperature of the cell
+    double um[SMAX], u0[SMAX], up[SMAX], T_s[SMAX], dT[SMAX], rT[SMAX];
+#pragma unroll
+    for (int s = 0; s < SMAX; s++) {
+        um[s] = u0[s] = up[s] = T_s[s] = dT[s] = rT[s] = 0.;
+        if (s < S) {
+            if (i >= 2) um[s] = p.u[idx_u(p, 0, col, s, i - 1)];                     // total_opacity(j) is 0 outside 1..N+1
+            u0[s] = p.u[idx_u(p, 0, col, s, i)];
+            if (i + 1 <= N + 1) up[s] = p.u[idx_u(p, 0, col, s, i + 1)];
+            if (i <= N) {
+                const SpeciesConst sc = p.sp[s];
+                const double u1 = p.u[idx_u(p, 0, col, s, i)], u2 = p.u[idx_u(p, 1, col, s, i)], u3 = p.u[idx_u(p, 2, col, s, i)];
+                Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
+                T_s[s] = p.Tsave ? p.Tsave[idx_s(p, col, s, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
+                dT[s] = 1 / dt;
+                rT[s] = T_s[s] / dt;
+                rT[s] += (p.dS[idx_s(p, col, s, i)] + 0.) / u1 / sc.cv;
+            }
+        }
+    }
+    auto Dcoef = [&](int ii, double Jc, double Jn, double toi, double toip) -> double {
+        const double dxc = (__ldg(p.x_i12 + ii + 1) - __ldg(p.x_i12 + ii));
         const double rhokr = sqrt(toi * toip);
         const double tau_inv = 1. / (dxc * rhokr);
         const double R = p.xi_rad * tau_inv * fabs(Jn - Jc) / (Jc + 1e-300);
-        return 1. * tau_inv * 1. * __ldg(p.surf + i) * flux_limiter(R);
+        return 1. * tau_inv * 1. * __ldg(p.surf + ii) * flux_limiter(R);
     };
-    double D_prev = 0, to_i = 0, to_ip = 0, Jcur = 0, Jnext = 0;
-    if (isJ && i0 < i1) {
-        to_ip = total_opacity(i0, lane);
-        Jnext = Jold(i0, lane);
-        const int im = i0 - 1;
-        if (im >= 1 && im <= N) D_prev = Dcoef(im, lane, Jold(im, lane), Jnext, total_opacity(im, lane), to_ip);
+    const bool coupled = (i <= N && !(i < p.ng || i >= N + 2 - p.ng));
+    constexpr int RECMAX = (4 + 2 * SMAX + 3) & ~3, TRECMAX = (2 + SMAX + 3) & ~3;
+    double rec[RECMAX];
+#pragma unroll
+    for (int k = 0; k < RECMAX; k++) rec[k] = 0.;
+    for (int b = 0; b < Bout; b++) {
+        // total (Rosseland) opacity of the cell and its neighbours: the largest species term
+        double to_m = 0, to_i = 0, to_ip = 0;
+#pragma unroll
+        for (int s = 0; s < SMAX; s++)
+            if (s < S) {
+                if (i - 1 >= 1) to_m = fmax(kapv(p, col, s, Bin + Bout + b, i - 1) * um[s], to_m);
+                if (i >= 1) to_i = fmax(kapv(p, col, s, Bin + Bout + b, i) * u0[s], to_i);      // i <= N+1 always
+                if (i + 1 <= N + 1) to_ip = fmax(kapv(p, col, s, Bin + Bout + b, i + 1) * up[s], to_ip);
+            }
+        const double Jcur = p.J[idx_J(p, col, b, i)];
+        const double Jnext = (i + 1 < N2) ? p.J[idx_J(p, col, b, i + 1)] : 0.;
+        double D_prev = 0;
+        if (i - 1 >= 1 && i - 1 <= N) D_prev = Dcoef(i - 1, p.J[idx_J(p, col, b, i - 1)], Jcur, to_m, to_i);
+        double l_rr = 0, u_rr = 0, rhs = 0, d = 0;
+        if (i >= 2 && i <= N + 1) { d = D_prev; l_rr = -D_prev; }
+        if (i <= N) {
+            const double tv = __ldg(p.vol + i) / (C_CLIGHT * dt);
+            d += tv;
+            rhs += tv * Jcur;
+        }
+        if (i >= 1 && i <= N) {
+            const double D_i = Dcoef(i, Jcur, Jnext, to_i, to_ip);
+            u_rr = -D_i; d += D_i;
+        }
+        if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
+        if (i == p.ng - 1 && p.use_planetary_temperature) {      // surface cell radiates at T_planet (radiation.cpp:451-472)
+            const double Tp = cst.T_planet;
+            double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp), log_spacing);
+            if (Tp < 0) Ssrc *= -1;
+            const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
+            double rhokr = smax(2. * (to_i * to_ip) / (to_i + to_ip), 4. / 3. / dxc);
+            rhokr = smin(0.5 * (to_i + to_ip), rhokr);
+            const double tau_inv = 1 / (dxc * rhokr);
+            const double R = p.xi_rad * tau_inv * fabs(Jnext - Jcur) / (Jnext + 1e-300);
+            const double Dc = flux_limiter(R) * tau_inv;
+            p.dcore[(size_t)col * Bout + b] = Dc;
+            const double Chi = 0.25;
+            const double sj = __ldg(p.surf + i);
+            l_rr = 0; d = 0.5 * (Dc + Chi) * sj; u_rr = -0.5 * (Dc - Chi) * sj; rhs = sj * Ssrc / (4 * C_PI);
+        }
+        if (p.closed_radiative_boundaries) {
+            if (i >= N2 - p.ng) { l_rr = -d; u_rr = 0; rhs = 0; }
+        } else if (i == N + 1) {
+            double f = __ldg(p.x_i12 + N) / __ldg(p.x_i12 + N + 1);
+            if (p.geometry == 0) f = 1;
+            else if (p.geometry == 2) f *= f;
+            l_rr = -f * d; u_rr = 0; rhs = 0;
+        }
+        // matter coupling: fac[s][b] = no_rad_trans * kappa_P * sigma T^3 / pi * planck fraction
+#pragma unroll
+        for (int s = 0; s < SMAX; s++)
+            if (s < S) {
+                double jt = 0., tj = 0.;
+                if (i <= N) {
+                    const double cv = p.sp[s].cv;
+                    const double Ts = T_s[s];
+                    const double kP = kapv(p, col, s, Bin + b, i);
+                    const double fac = 1. * p.no_rad_trans * kP * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
+                                       planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], Ts, log_spacing);
+                    dT[s] += 16 * C_PI * fac / cv;
+                    rT[s] += 12 * C_PI * fac * Ts / cv;
+                    tj = -4 * C_PI * kP * p.no_rad_trans / cv;
+                    if (coupled) {
+                        const double rho = u0[s];
+                        const double vj = __ldg(p.vol + i);
+                        d += vj * rho * kP * p.no_rad_trans;
+                        jt = -4 * vj * rho * fac;
+                        rhs -= 3 * vj * rho * fac * Ts;
+                    }
+                }
+                rec[4 + s] = jt;
+                rec[4 + S + s] = tj;
+            }
+        rec[0] = d; rec[1] = l_rr; rec[2] = u_rr; rec[3] = rhs;
+        store_record<RECMAX>(cf + b * fd.W, rec, fd.W);
     }
-    for (int i = i0; i < i1; i++) {
-        double* cf = p.fcoef + ((size_t)col * N2 + i) * fd.NC;
-        // primitive density and temperature of every species in this cell, once (lanes 0..S-1)
-        if (lane < S && i <= N) {
-            const SpeciesConst sc = p.sp[lane];
-            const double u1 = p.u[idx_u(p, 0, col, lane, i)], u2 = p.u[idx_u(p, 1, col, lane, i)], u3 = p.u[idx_u(p, 2, col, lane, i)];
-            Prim3 q = cons_to_prim(u1, u2, u3, sc.gm1);
-            rho_s[lane] = q.rho;
-            T_s[lane] = p.Tsave ? p.Tsave[idx_s(p, col, lane, i)] : eint_of(q.p, q.rho, sc.gm1) / sc.cv;
-        }
-        __syncwarp();
-        // fac[s][b] = no_rad_trans * kappa_P * sigma T^3 / pi * planck fraction, and the T-row terms built from it
-        if (isJ && i <= N) {
-            for (int s = 0; s < S; s++) {
-                const double cv = p.sp[s].cv;
-                const double Ts = T_s[s];
-                const double kP = kapv(p, col, s, Bin + lane, i);
-                const double fac = 1. * p.no_rad_trans * kP * C_SIGMA_RAD * Ts * Ts * Ts / C_PI *
-                                   planck_integral3(p, p.l_i_out[lane], p.l_i_out[lane + 1], Ts, log_spacing);
-                facs[s * Bout + lane] = fac;
-                dterm[s * Bout + lane] = 16 * C_PI * fac / cv;
-                rterm[s * Bout + lane] = 12 * C_PI * fac * Ts / cv;
-                cf[fd.o_TJ + s * Bout + lane] = -4 * C_PI * kP * p.no_rad_trans / cv;
-            }
-        } else if (isJ) {
-            for (int s = 0; s < S; s++) cf[fd.o_TJ + s * Bout + lane] = 0.;
-        }
-        __syncwarp();
-        double l_rr = 0, u_rr = 0, rhs = 0, dd = 0;
-        if (isJ) {
-            const int b = lane;
-            Jcur = Jnext;
-            Jnext = (i + 1 < N2) ? Jold(i + 1, b) : 0.;
-            to_i = to_ip;
-            to_ip = total_opacity(i + 1, b);
-            double d = 0;
-            if (i >= 2 && i <= N + 1) { d = D_prev; l_rr = -D_prev; }
+    // T rows: collisional T_i - T_j coupling (radiation.cpp:589-615, source.cpp:656-674), then the row itself
+#pragma unroll
+    for (int s = 0; s < SMAX; s++)
+        if (s < S) {
+            double trec[TRECMAX];
+#pragma unroll
+            for (int k = 0; k < TRECMAX; k++) trec[k] = 0.;
+            double d = 0., rhs = 0.;
             if (i <= N) {
-                const double tv = __ldg(p.vol + i) / (C_CLIGHT * dt);
-                d += tv;
-                rhs += tv * Jcur;
-            }
-            double D_i = 0;
-            if (i >= 1 && i <= N) {
-                D_i = Dcoef(i, b, Jcur, Jnext, to_i, to_ip);
-                u_rr = -D_i; d += D_i;
-            }
-            D_prev = D_i;
-            if (i < p.ng) { l_rr = 0; u_rr = -d; rhs = 0; }
-            if (i == p.ng - 1 && p.use_planetary_temperature) {      // surface cell radiates at T_planet (radiation.cpp:451-472)
-                const double Tp = cst.T_planet;
-                double Ssrc = C_SIGMA_RAD * pow(Tp, 4.) * planck_integral3(p, p.l_i_out[b], p.l_i_out[b + 1], fabs(Tp), log_spacing);
-                if (Tp < 0) Ssrc *= -1;
-                const double dxc = (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
-                double rhokr = smax(2. * (to_i * to_ip) / (to_i + to_ip), 4. / 3. / dxc);
-                rhokr = smin(0.5 * (to_i + to_ip), rhokr);
-                const double tau_inv = 1 / (dxc * rhokr);
-                const double R = p.xi_rad * tau_inv * fabs(Jnext - Jcur) / (Jnext + 1e-300);
-                const double Dc = flux_limiter(R) * tau_inv;
-                p.dcore[(size_t)col * Bout + b] = Dc;
-                const double Chi = 0.25;
-                const double sj = __ldg(p.surf + i);
-                l_rr = 0; d = 0.5 * (Dc + Chi) * sj; u_rr = -0.5 * (Dc - Chi) * sj; rhs = sj * Ssrc / (4 * C_PI);
-            }
-            if (p.closed_radiative_boundaries) {
-                if (i >= N2 - p.ng) { l_rr = -d; u_rr = 0; rhs = 0; }
-            } else if (i == N + 1) {
-                double f = __ldg(p.x_i12 + N) / __ldg(p.x_i12 + N + 1);
-                if (p.geometry == 0) f = 1;
-                else if (p.geometry == 2) f *= f;
-                l_rr = -f * d; u_rr = 0; rhs = 0;
-            }
-            const bool coupled = (i <= N && !(i < p.ng || i >= N + 2 - p.ng));
-            for (int s = 0; s < S; s++) {
-                double jt = 0.;
-                if (coupled) {
-                    const double rho = rho_s[s], Ts = T_s[s];
-                    const double fac = facs[s * Bout + b];
-                    const double vj = __ldg(p.vol + i);
-                    d += vj * rho * kapv(p, col, s, Bin + b, i) * p.no_rad_trans;
-                    jt = -4 * vj * rho * fac;
-                    rhs -= 3 * vj * rho * fac * Ts;
-                }
-                cf[fd.o_JT + b * S + s] = jt;
-            }
-            dd = d;
-        } else if (isT) {
-            const int s = sT;
-            for (int sj = 0; sj < S; sj++) cf[fd.o_TT + s * S + sj] = 0.;
-            if (i <= N) {
-                const SpeciesConst sc = p.sp[s];
-                const double u1 = rho_s[s], Ts = T_s[s];
-                double d = 1 / dt;
-                rhs = Ts / dt;
-                rhs += (p.dS[idx_s(p, col, s, i)] + 0.) / u1 / sc.cv;
-                for (int b = 0; b < Bout; b++) {
-                    d += dterm[s * Bout + b];
-                    rhs += rterm[s * Bout + b];
-                }
-                // collisional T_i - T_j coupling (radiation.cpp:589-615, source.cpp:656-674)
+                d = dT[s]; rhs = rT[s];
                 if (p.use_collisional_heating && S > 1) {
+                    const SpeciesConst sc = p.sp[s];
+                    const double u1 = u0[s], Ts = T_s[s];
                     double tot0 = 0;
                     if (i >= 1) for (int ss = 0; ss < S; ss++) tot0 = fmax(kapv(p, col, ss, Bin + Bout + 0, i) * p.u[idx_u(p, 0, col, ss, i)], tot0);
                     const double tau = tot0 * (__ldg(p.x_i12 + i + 1) - __ldg(p.x_i12 + i));
                     const double damp = (tau < 1e3) ? 1. : 1.e-4;
                     double diag_sum = 0, self = 0;
-                    for (int sj = 0; sj < S; sj++) {
+                    for (int sj = 0; sj < S; sj++) {          // rolled: density and temperature of species sj are re-derived
                         const SpeciesConst cj = p.sp[sj];
-                        const double w1 = rho_s[sj], Tj = T_s[sj];
+                        const double w1 = p.u[idx_u(p, 0, col, sj, i)];
+                        const double v2 = p.u[idx_u(p, 1, col, sj, i)], v3 = p.u[idx_u(p, 2, col, sj, i)];
+                        const Prim3 qj = cons_to_prim(w1, v2, v3, cj.gm1);
+                        const double Tj = p.Tsave ? p.Tsave[idx_s(p, col, sj, i)] : eint_of(qj.p, qj.rho, cj.gm1) / cj.cv;
                         double fc = p.fric_mask[s * S + sj] * alpha_pair(p, s, sj, S, sc, cj, u1, w1, w1 / cj.mass, Ts, Tj, tnow);
                         fc *= 3 * C_KB / (sc.cv * (sc.mass + cj.mass));
                         diag_sum += fc;
+                        const double off = 0. - fc * damp;
+#pragma unroll
+                        for (int k = 0; k < SMAX; k++) if (k == sj && sj != s) trec[2 + k] = off;
                         if (sj == s) self = fc;
-                        else cf[fd.o_TT + s * S + sj] = 0. - fc * damp;
                     }
                     d -= (self - diag_sum) * damp;
                 }
-                dd = d;
             }
+            trec[0] = d; trec[1] = rhs;
+            store_record<TRECMAX>(cf + fd.o_T + s * fd.V, trec, fd.V);
         }
-        if (lane < fd.R) {
-            cf[fd.o_D + lane] = dd;
-            cf[fd.o_L + lane] = l_rr;
-            cf[fd.o_U + lane] = u_rr;
-            cf[fd.o_B + lane] = rhs;
-        }
-        if (lane == 0 && ((fd.o_TT + S * S) & 1)) cf[fd.NC - 1] = 0.;
-        __syncwarp();
-    }
 }
 
 // ---- the sequential sweep: one warp per column, LU in registers ---------------------------------------------------------------------
@@ -476,7 +476,7 @@ __device__ __forceinline__ void lu_phase(double (&a)[RI][RI], const LuCtx<RI>& c
 }
 
 template <int RI>
-__global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p) {
+__global__ void __launch_bounds__(32, FULL_LU_CTAS_PER_SM) k_full_lu(DevParams p) {
     AIO_DYN_SMEM(double, sm);
     const int lane = threadIdx.x & 31;
     const int col = blockIdx.x;
@@ -518,7 +518,9 @@ __global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p
         for (int ii = 0; ii < RI; ii++) {
             const int r = rg + 4 * ii;
             const bool rowJ = r < Bout, rowT = (r >= Bout && r < n);
-            const double Dr = cf[fd.o_D + r], Lr = cf[fd.o_L + r], Ur = cf[fd.o_U + r], Br = cf[fd.o_B + r];
+            // row r of the stream: a band record (J rows), a species record (T rows), nothing (padding rows)
+            const double* rr = rowJ ? cf + r * fd.W : cf + fd.o_T + (rowT ? r - Bout : 0) * fd.V;
+            const double Dr = (r < n) ? rr[0] : 0., Lr = rowJ ? rr[1] : 0., Ur = rowJ ? rr[2] : 0., Br = rowJ ? rr[3] : (rowT ? rr[1] : 0.);
             const bool useX = rowJ && (i > 0) && (Lr != 0.);
 #pragma unroll
             for (int j = 0; j < LB; j++) {
@@ -528,10 +530,10 @@ __global__ void __launch_bounds__(32, (RI == 6) ? 14 : 16) k_full_lu(DevParams p
                     if (cc < Bout) {
                         val = (cc == r) ? Dr : 0.;
                         if (useX) val = d_sub(val, d_mul(Lr, c.Y[r * c.LDY + cc]));
-                    } else if (cc < n) val = cf[fd.o_JT + r * S + (cc - Bout)];
+                    } else if (cc < n) val = rr[4 + (cc - Bout)];
                 } else if (rowT) {
-                    if (cc < Bout) val = cf[fd.o_TJ + (r - Bout) * Bout + cc];
-                    else if (cc < n) val = (cc == r) ? Dr : cf[fd.o_TT + (r - Bout) * S + (cc - Bout)];
+                    if (cc < Bout) val = cf[cc * fd.W + 4 + S + (r - Bout)];
+                    else if (cc < n) val = (cc == r) ? Dr : rr[2 + (cc - Bout)];
                 }
                 a[ii][j] = val;
             }

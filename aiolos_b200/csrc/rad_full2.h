@@ -9,8 +9,12 @@ namespace aio {
 
 struct Full2Dims {
     int n, R, RI;
-    int NC;                        // doubles per cell in the coefficient stream (even => 16-byte blocks)
-    int o_D, o_L, o_U, o_B, o_JT, o_TJ, o_TT;
+    // Coefficient stream of one cell (k_full_asm2 -> k_full_lu): Bout band records of W doubles
+    //   [D, L, U, B, JT(s = 0..S-1), TJ(s = 0..S-1), pad]     D: diagonal of d_i, L / U: the (diagonal) l_i / u_i entry, B: rhs,
+    //                                                          JT = d_i(J_b, T_s), TJ = d_i(T_s, J_b)
+    // followed by S species records of V doubles  [D, B, TT(t = 0..S-1), pad]  (TT: off-diagonal T-T couplings; TT(s, s) = 0).
+    // W and V are multiples of 4 doubles, so a thread writes a record as whole 32-byte sectors.
+    int W, V, o_T, NC;
     int LDXg, XB;                  // row stride (odd => conflict-free lane = row reads) and block size (even) of X_i in HBM
     int LDU, LDY;
     int sm_warp;                   // doubles of shared memory per column in k_full_lu
@@ -23,9 +27,8 @@ __host__ __device__ inline Full2Dims full2_dims_ri(int Bout, int S, int RI) {
     d.n = Bout + S;
     d.RI = RI;
     d.R = 4 * d.RI;
-    d.o_D = 0; d.o_L = d.R; d.o_U = 2 * d.R; d.o_B = 3 * d.R;
-    d.o_JT = 4 * d.R; d.o_TJ = d.o_JT + Bout * S; d.o_TT = d.o_TJ + S * Bout;
-    d.NC = d.o_TT + S * S; d.NC += d.NC & 1;
+    d.W = (4 + 2 * S + 3) & ~3; d.V = (2 + S + 3) & ~3;
+    d.o_T = Bout * d.W; d.NC = d.o_T + S * d.V;
     d.LDXg = (Bout + 1) | 1;
     d.XB = d.n * d.LDXg; d.XB += d.XB & 1;
     d.LDU = d.R + 2; d.LDY = d.R;
@@ -55,10 +58,12 @@ __host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
     return full2_dims_ri(Bout, S, (n <= 8) ? 2 : (n <= 16) ? 4 : 6);
 }
 
-constexpr int FULL_ASM_WARPS = 8;
 // cudaFuncSetAttribute for the four kernels; launch of one radiation step on `stream`
-void full2_configure(int RI, size_t smem_lu, size_t smem_asm);
-void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_asm, void* stream);
+#ifndef FULL_LU_CTAS_PER_SM
+#define FULL_LU_CTAS_PER_SM 16        // resident single-warp CTAs per SM k_full_lu is compiled for (128 registers)
+#endif
+void full2_configure(int RI, size_t smem_lu);
+void full2_launch(const DevParams& p, int RI, size_t smem_lu, void* stream);
 
 void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, double* x);
 

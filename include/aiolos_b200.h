@@ -64,10 +64,11 @@ int aio_device_count(void);
 int aio_device_peaks(int device, double* fp64_tflops, double* copy_gbs);
 
 /* Kernel-level known-answer hook for the coupled J_b / T_s block-tridiagonal solve (block_tridiag_solve.h:57-130): runs the
- * product's block-Thomas sweep on caller-supplied block rows.  coef: [ncols][num_cells2][NC] doubles, per cell
- *   D[R] L[R] U[R] B[R] JT[bands_out][num_species] TJ[num_species][bands_out] TT[num_species][num_species] (+1 pad if odd)
- * with R = 8 / 16 / 24 >= n = bands_out + num_species (D: diagonal of d_i; L, U: the diagonal l_i / u_i entries of the J
- * rows; B: right-hand side; JT / TJ / TT: the J-T, T-J and off-diagonal T-T entries of d_i).  x: [ncols][num_cells2][n]. */
+ * product's block-Thomas sweep on caller-supplied block rows.  coef: [ncols][num_cells2][NC] doubles; per cell bands_out
+ * band records of W doubles  [D, L, U, B, JT(s = 0..S-1), TJ(s = 0..S-1), pad]  followed by num_species species records of V
+ * doubles  [D, B, TT(t = 0..S-1), pad], W = (4 + 2 S) and V = (2 + S) rounded up to multiples of 4, NC = bands_out W + S V
+ * (D: diagonal of d_i; L, U: the diagonal l_i / u_i entry of the J row; B: right-hand side; JT = d_i(J_b, T_s), TJ = d_i(T_s,
+ * J_b), TT = off-diagonal d_i(T_s, T_t)); n = bands_out + num_species <= 24.  x: [ncols][num_cells2][n]. */
 int aio_selftest_block_thomas(int ncols, int num_cells2, int bands_out, int num_species, const double* coef, double* x);
 
 int aio_create(const char* dir, const char* par, const char* spc, int ncols, const aio_override* ov, int n_ov,

@@ -63,36 +63,50 @@ def solve_block_tridiag(l, d, u, rhs):
 
 
 def stream_dims(bands_out, num_species):
-    """Offsets of the per-cell coefficient stream the device sweep reads (aiolos_b200/csrc/rad_full2.h: full2_dims)."""
+    """Geometry of the per-cell coefficient stream the device sweep reads (aiolos_b200/csrc/rad_full2.h, Full2Dims):
+    bands_out band records of W doubles [D, L, U, B, JT(s)..., TJ(s)..., pad], then num_species species records of V doubles
+    [D, B, TT(t)..., pad]; W and V are multiples of 4."""
     n = bands_out + num_species
-    R = 8 if n <= 8 else 16 if n <= 16 else 24
-    o = {"n": n, "R": R, "D": 0, "L": R, "U": 2 * R, "B": 3 * R, "JT": 4 * R}
-    o["TJ"] = o["JT"] + bands_out * num_species
-    o["TT"] = o["TJ"] + num_species * bands_out
-    nc = o["TT"] + num_species * num_species
-    o["NC"] = nc + (nc & 1)
-    return o
+    W = (4 + 2 * num_species + 3) & ~3
+    V = (2 + num_species + 3) & ~3
+    return {"n": n, "W": W, "V": V, "T": bands_out * W, "NC": bands_out * W + num_species * V}
+
+
+def pack_stream(D, L, U, Bv, JT, TJ, TT, bands_out, num_species):
+    """One cell's coefficients (D, Bv: [n]; L, U: [bands_out]; JT: [bands_out][S]; TJ: [S][bands_out]; TT: [S][S]) as the stream."""
+    o = stream_dims(bands_out, num_species)
+    B, S, W, V = bands_out, num_species, o["W"], o["V"]
+    c = np.zeros(o["NC"])
+    for b in range(B):
+        c[b * W:b * W + 4] = [D[b], L[b], U[b], Bv[b]]
+        c[b * W + 4:b * W + 4 + S] = JT[b]
+        c[b * W + 4 + S:b * W + 4 + 2 * S] = TJ[:, b]
+    for s in range(S):
+        r = o["T"] + s * V
+        c[r], c[r + 1] = D[B + s], Bv[B + s]
+        c[r + 2:r + 2 + S] = TT[s]
+        c[r + 2 + s] = 0.0
+    return c
 
 
 def dense_blocks(coef, bands_out, num_species):
     """Expand one column's coefficient stream [cells][NC] into the dense l, d, u blocks and right-hand sides the reference's
     update_fluxes_FLD would hand to BlockTriDiagSolver (radiation.cpp:407-615: l_i / u_i carry only the J-J diagonal)."""
     o = stream_dims(bands_out, num_species)
-    cells, n, B, S = coef.shape[0], o["n"], bands_out, num_species
+    cells, n, B, S, W, V = coef.shape[0], o["n"], bands_out, num_species, o["W"], o["V"]
     l = np.zeros((cells, n, n)); d = np.zeros((cells, n, n)); u = np.zeros((cells, n, n)); rhs = np.zeros((cells, n))
     for i in range(cells):
         c = coef[i]
-        for r in range(n):
-            d[i, r, r] = c[o["D"] + r]
-            rhs[i, r] = c[o["B"] + r]
-        for r in range(B):
-            l[i, r, r] = c[o["L"] + r]
-            u[i, r, r] = c[o["U"] + r]
+        for b in range(B):
+            rec = c[b * W:(b + 1) * W]
+            d[i, b, b], l[i, b, b], u[i, b, b], rhs[i, b] = rec[0], rec[1], rec[2], rec[3]
             for s in range(S):
-                d[i, r, B + s] = c[o["JT"] + r * S + s]
-                d[i, B + s, r] = c[o["TJ"] + s * B + r]
+                d[i, b, B + s] = rec[4 + s]
+                d[i, B + s, b] = rec[4 + S + s]
         for s in range(S):
+            rec = c[o["T"] + s * V:o["T"] + (s + 1) * V]
+            d[i, B + s, B + s], rhs[i, B + s] = rec[0], rec[1]
             for t in range(S):
                 if s != t:
-                    d[i, B + s, B + t] = c[o["TT"] + s * S + t]
+                    d[i, B + s, B + t] = rec[2 + t]
     return l, d, u, rhs

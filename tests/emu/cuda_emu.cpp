@@ -44,7 +44,7 @@ void sync_warp() { yield(WAIT_WARP); }
 void run_grid(void (*thunk)(void*), void* args, dim3 grid, dim3 block, size_t smem) {
     const int NT = (int)block.x;
     g_thunk = thunk; g_args = args;
-    gDim = {grid.x, 1, 1}; bDim = {block.x, 1, 1};
+    gDim = {grid.x, grid.y, 1}; bDim = {block.x, 1, 1};
     if ((int)fibers.size() < NT) {
         size_t old = fibers.size();
         fibers.resize(NT);
@@ -52,8 +52,9 @@ void run_grid(void (*thunk)(void*), void* args, dim3 grid, dim3 block, size_t sm
     }
     std::vector<unsigned char> sm(smem + 16);
     dyn_smem_bytes = smem;
-    for (unsigned b = 0; b < grid.x; b++) {
-        bIdx = {b, 0, 0};
+    for (unsigned bb = 0; bb < grid.x * grid.y; bb++) {
+        const unsigned b = bb % grid.x;
+        bIdx = {b, bb / grid.x, 0};
         memset(sm.data(), 0xff, sm.size());              // all-ones doubles are NaNs
         dyn_smem = (void*)(((uintptr_t)sm.data() + 15) & ~(uintptr_t)15);
         for (int t = 0; t < NT; t++) {

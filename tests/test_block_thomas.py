@@ -11,7 +11,7 @@ import aiolos_b200 as A
 from conftest import ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from block_thomas import dense_blocks, solve_block_tridiag, stream_dims  # noqa: E402
+from block_thomas import dense_blocks, pack_stream, solve_block_tridiag, stream_dims  # noqa: E402
 
 
 def make_stream(seed, ncols, cells, B, S, mode):
@@ -20,30 +20,22 @@ def make_stream(seed, ncols, cells, B, S, mode):
     side in the last cell, as the reference's last ghost cell has, and exactly-zero right-hand sides)."""
     rng = np.random.default_rng(seed)
     o = stream_dims(B, S)
-    n, R = o["n"], o["R"]
+    n = o["n"]
     coef = np.zeros((ncols, cells, o["NC"]))
     for c in range(ncols):
         for i in range(cells):
-            cf = coef[c, i]
-            diag = rng.uniform(2.0, 4.0, n) * (1.0 if mode == "dominant" else 0.05)
-            cf[o["D"]:o["D"] + n] = diag * (n if mode == "dominant" else 1.0)
-            if i > 0:
-                cf[o["L"]:o["L"] + B] = -rng.uniform(0.2, 1.0, B)
-            if i + 1 < cells:
-                cf[o["U"]:o["U"] + B] = -rng.uniform(0.2, 1.0, B)
-            cf[o["B"]:o["B"] + n] = rng.uniform(-1.0, 1.0, n)
-            cf[o["JT"]:o["JT"] + B * S] = rng.uniform(-1.0, 1.0, B * S)
-            cf[o["TJ"]:o["TJ"] + S * B] = rng.uniform(-1.0, 1.0, S * B)
-            tt = rng.uniform(-0.5, 0.5, (S, S)); np.fill_diagonal(tt, 0.0)
-            cf[o["TT"]:o["TT"] + S * S] = tt.ravel()
+            D = rng.uniform(2.0, 4.0, n) * (n if mode == "dominant" else 0.05)
+            L = -rng.uniform(0.2, 1.0, B) if i > 0 else np.zeros(B)
+            U = -rng.uniform(0.2, 1.0, B) if i + 1 < cells else np.zeros(B)
+            Bv = rng.uniform(-1.0, 1.0, n)
+            JT = rng.uniform(-1.0, 1.0, (B, S)); TJ = rng.uniform(-1.0, 1.0, (S, B))
+            TT = rng.uniform(-0.5, 0.5, (S, S))
             if mode == "zeros":
                 if i % 3 == 1:
-                    cf[o["B"]:o["B"] + n] = 0.0
+                    Bv[:] = 0.0
                 if i == cells - 1:                     # all-zero T rows with zero right-hand side (SURVEY 0.6)
-                    cf[o["D"] + B:o["D"] + n] = 0.0
-                    cf[o["B"] + B:o["B"] + n] = 0.0
-                    cf[o["TJ"]:o["TJ"] + S * B] = 0.0
-                    cf[o["TT"]:o["TT"] + S * S] = 0.0
+                    D[B:] = 0.0; Bv[B:] = 0.0; TJ[:] = 0.0; TT[:] = 0.0
+            coef[c, i] = pack_stream(D, L, U, Bv, JT, TJ, TT, B, S)
     return coef
 
 

@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "c3 or c6 or n1 or n2 or t1 or p1 or g1 or full" > $OUT/gpu_tests_c3_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/gpu_tests_c3_$TAG.log
 timeout 300 python tools/time_case.py c3_searth_22b --ncols 4096 --spinup 12 --steps 10 > $OUT/time_c3_$TAG.json 2>&1
-timeout 300 python tools/time_case.py c3_searth_22b --ncols 4096 --spinup 12 --steps 10 --opt full_lu=tile2 > $OUT/time_c3_tile2_$TAG.json 2>&1
+timeout 300 python tools/time_case.py c3_searth_22b --ncols 4096 --spinup 12 --steps 10 --ncols 2072 > $OUT/time_c3_2072_$TAG.json 2>&1
 timeout 300 python tools/time_case.py c3_searth_22b --ncols 512 --spinup 12 --steps 10 > $OUT/time_c3_512_$TAG.json 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_c3_$TAG.csv \
     python tools/time_case.py c3_searth_22b --ncols 4096 --spinup 2 --steps 2 > $OUT/ncu_launch_c3_$TAG.log 2>&1
