@@ -110,6 +110,47 @@ static void check_supported(const Problem& q) {
     }
 }
 
+// Everything the kernels take from column 0 (DevParams scalars, species constants, opacity tables, band layout) must be the
+// same in every column: a per-column .par override may only change what the engine keeps per column -- the initial state
+// (u, eint_last, phi, Jrad_FLD, dS_band), the irradiation (solar_heating_final, i.e. PARI_UVSTAR / PARI_XSTAR / PARI_LUM...),
+// the clock (dt, cflfactor, t_max, timestep_rad2) and T_planet.  Returns the name of the first field that differs.
+static std::string ensemble_mismatch(const Problem& a, const Problem& b) {
+#define CMP(f) if (!(a.f == b.f)) return #f
+    CMP(num_ghosts); CMP(order); CMP(geometry); CMP(problem_number); CMP(type_of_grid);
+    CMP(use_rad_fluxes); CMP(use_tides); CMP(use_self_gravity); CMP(use_linear_gravity); CMP(friction_solver);
+    CMP(photochemistry_level); CMP(use_collisional_heating); CMP(use_drag_predictor_step); CMP(do_hydrodynamics);
+    CMP(closed_radiative_boundaries); CMP(use_planetary_temperature); CMP(couple_J_into_T); CMP(solve_for_j);
+    CMP(radiation_matter_equilibrium_test); CMP(use_convective_fluxes); CMP(update_coll_frequently); CMP(use_avg_temperature);
+    CMP(use_total_pressure); CMP(collision_model); CMP(opacity_model);
+    CMP(max_timestep_change); CMP(dt_min_init); CMP(dt_max); CMP(energy_epsilon); CMP(CFL_break_time); CMP(start_hydro_time);
+    CMP(planet_position); CMP(planet_semimajor); CMP(star_mass); CMP(rs); CMP(rs_time); CMP(domain_min); CMP(domain_max); CMP(K_zz_init);
+    CMP(alpha_collision); CMP(alpha_collision_ions); CMP(coll_rampup_time); CMP(init_coll_factor);
+    CMP(radiation_rampup_time); CMP(init_radiation_factor); CMP(bond_albedo); CMP(xi_rad); CMP(no_rad_trans);
+    CMP(photocooling_expansion); CMP(temperature_floor); CMP(max_temperature);
+    CMP(const_opacity_solar_factor); CMP(const_opacity_rosseland_factor); CMP(const_opacity_planck_factor);
+    CMP(R_star); CMP(T_star); CMP(T_int); CMP(core_cv); CMP(right_extrap_press_multiplier); CMP(max_mdot);
+    CMP(lT_spacing); CMP(avg_temperature_t0); CMP(avg_temperature_t1); CMP(num_plancks);
+    CMP(x_i12); CMP(dx); CMP(vol); CMP(surf); CMP(l_i_in); CMP(l_i_out); CMP(photon_energies); CMP(planck_matrix);
+    CMP(highenergy_switch); CMP(friction_coeff_mask); CMP(inv_totmasses); CMP(resonant_pair_matrix);
+    bool mass_matters = a.use_self_gravity != 0;
+    for (size_t s = 0; s < a.species.size(); s++) {
+        const SpeciesData &x = a.species[s], &y = b.species[s];
+#define CMPS(f) if (!(x.f == y.f)) return "species[" + std::to_string(s) + "]." #f
+        CMPS(mass_amu); CMPS(static_charge); CMPS(is_dust_like); CMPS(cv); CMPS(gamma_adiabat); CMPS(degrees_of_freedom);
+        CMPS(const_T_space); CMPS(const_opacity); CMPS(boundary_left); CMPS(boundary_right); CMPS(USE_WAVE); CMPS(WAVE_AMPLITUDE);
+        CMPS(WAVE_PERIOD); CMPS(initial_fraction); CMPS(density_excess);
+        CMPS(opacity_avg_solar); CMPS(opacity_avg_planck); CMPS(opacity_avg_rosseland);
+        CMPS(opa_pgrid); CMPS(opa_tgrid); CMPS(opa_grid_solar_log); CMPS(opa_grid_planck_log); CMPS(opa_grid_rosseland_log);
+        for (int k = 0; k < 3; k++) if (x.SHOCK_TUBE_UL[k] != y.SHOCK_TUBE_UL[k] || x.SHOCK_TUBE_UR[k] != y.SHOCK_TUBE_UR[k] || x.BACKGROUND_U[k] != y.BACKGROUND_U[k])
+            return "species[" + std::to_string(s) + "] shock-tube / background state";
+#undef CMPS
+        if (x.boundary_left == 5 || x.boundary_right == 5) mass_matters = true;      // giantplanet BC reads planet_mass in the kernel
+    }
+    if (mass_matters) CMP(planet_mass);     // otherwise the mass only shapes phi and the initial state, both kept per column
+#undef CMP
+    return "";
+}
+
 Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     if (cols.empty()) throw std::runtime_error("empty ensemble");
     const Problem& q0 = cols[0];
@@ -118,6 +159,12 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
         if (q.num_cells != q0.num_cells || q.num_species != q0.num_species || q.num_bands_in != q0.num_bands_in ||
             q.num_bands_out != q0.num_bands_out || q.order != q0.order || q.x_i != q0.x_i)
             throw std::runtime_error("ensemble columns must share grid, species count and band layout");
+        if (&q != &q0) {
+            const std::string f = ensemble_mismatch(q0, q);
+            if (!f.empty())
+                throw std::runtime_error("unsupported configuration: a per-column override changes '" + f + "', which the engine reads from "
+                                         "column 0 for the whole ensemble (per-column: initial state, irradiation, dt / t_max, T_planet)");
+        }
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -497,17 +544,27 @@ double Engine::advance(long long nsteps, bool timed) {
 }
 
 // Run until every column has finished (t >= t_max or crashed), polling the per-column clocks every `chunk` steps.
+// Returns the steps actually taken: the largest per-column step count since entry (the reference's `steps` of execute()).
 long long Engine::run_to_tmax(long long chunk, long long max_total) {
-    long long done = 0;
+    fetch_states();
+    std::vector<long long> steps0(im->h_cs.size());
+    for (size_t c = 0; c < im->h_cs.size(); c++) steps0[c] = im->h_cs[c].steps;
+    long long done = 0, taken = 0;
     while (done < max_total) {
-        advance(chunk, false);
-        done += chunk;
+        const long long k = std::min(chunk, max_total - done);     // never past max_total: execute() stops exactly at maxsteps
+        advance(k, false);
+        done += k;
         fetch_states();
         bool any = false;
-        for (auto& c : im->h_cs) if (c.status == COL_OK && c.t < c.t_max) { any = true; break; }
+        taken = 0;
+        for (size_t c = 0; c < im->h_cs.size(); c++) {
+            const ColState& cs = im->h_cs[c];
+            taken = std::max(taken, (long long)cs.steps - steps0[c]);
+            if (cs.status == COL_OK && cs.t < cs.t_max) any = true;
+        }
         if (!any) break;
     }
-    return done;
+    return taken;
 }
 
 void Engine::fetch_states() {

@@ -23,7 +23,13 @@ extern "C" {
 
 typedef struct aio_ensemble aio_ensemble;
 
-/* Per-column override of one .par key (ensemble sweeps).  column < 0 applies to every column. */
+/* Per-column override of one .par key (ensemble sweeps).  column < 0 applies to every column.
+ * A column-specific override may change what the engine keeps per column: the initial state the constructor builds (u,
+ * eint_last, phi, Jrad_FLD, dS_band), the irradiation (PARI_UVSTAR, PARI_XSTAR, PARI_LUM..., i.e. solar_heating_final), the
+ * clock (dt, CFL factor, PARI_TIME_TMAX) and T_planet; PARI_PLANET_MASS as long as neither self-gravity nor a giantplanet
+ * boundary reads the mass inside the kernels.  Every other quantity (switches, opacities, species constants, band layout,
+ * grid) is shared by the ensemble: an override that makes it differ between columns is refused with AIO_ERR_UNSUPPORTED,
+ * naming the field. */
 typedef struct aio_override {
     int column;
     const char* key;      /* a PARI_* name exactly as in the .par file, e.g. "PARI_UVSTAR" */
@@ -83,7 +89,8 @@ int aio_dims(aio_ensemble* e, int* ncols, int* num_cells, int* num_species, int*
 /* Advance every column by up to max_steps further steps (a column stops at its own t_max or when it soft-crashes).
  * device_ms (may be NULL) receives the CUDA-event time of the launch sequence on the ensemble's stream. */
 int aio_advance(aio_ensemble* e, long long max_steps, double* device_ms);
-/* Run until every column reached min(t_max, t_stop) or crashed; returns the number of step launches in *steps_done. */
+/* c_Sim::execute(): run until every column reached min(t_max, t_stop), crashed, or took max_steps steps (max_steps <= 0: no
+ * limit; never exceeded).  *steps_done receives the steps taken (the largest per-column count). */
 int aio_run(aio_ensemble* e, double t_stop, long long max_steps, long long* steps_done);
 int aio_set_tmax(aio_ensemble* e, int column, double t_max);   /* column < 0: all */
 /* Advance nsteps steps with a CUDA event between the kernel launches; ms3 receives the average device milliseconds per

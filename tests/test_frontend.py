@@ -120,3 +120,29 @@ def test_reader_semantics(emu_lib, rundir, monkeypatch):
     with pytest.raises(A.AiolosError) as ei:
         A.Ensemble.from_files(d, "chem.par", "", lib=emu_lib)
     assert ei.value.code == -3 and "PHOTOCHEM_LEVEL" in str(ei.value)
+
+
+def test_per_column_override_of_shared_quantity_is_refused(emu_lib, rundir, monkeypatch):
+    """The engine reads switches, opacities and species constants from column 0: an override that would make them differ between
+    columns must be refused (naming the field), not silently run column 0's physics."""
+    monkeypatch.chdir(rundir)
+    d, par, _ = DECKS["c4_dynamic3_euv"]
+    with pytest.raises(A.AiolosError) as ei:
+        A.Ensemble.from_files(d, par, "", ncols=2, overrides=[(1, "BOND_ALBEDO", "0.3")], lib=emu_lib)
+    assert ei.value.code == -3 and "bond_albedo" in str(ei.value)
+    with pytest.raises(A.AiolosError) as ei:
+        A.Ensemble.from_files(d, par, "", ncols=2, overrides=[(1, "PARI_CONST_OPAC", "2.0")], lib=emu_lib)
+    assert ei.value.code == -3
+    # the same override applied to every column is fine, and so is a per-column planet mass without self-gravity
+    A.Ensemble.from_files(d, par, "", ncols=2, overrides=[(-1, "BOND_ALBEDO", "0.3")], lib=emu_lib)
+    e = A.Ensemble.from_files(d, par, "", ncols=2, overrides=[(1, "PARI_PLANET_MASS", "300.")], lib=emu_lib)
+    assert not np.array_equal(e.get("phi", 0), e.get("phi", 1))
+
+
+def test_execute_stops_exactly_at_max_steps(emu_lib):
+    """c_Sim::execute() stops at maxsteps (advection.cpp:60); steps_done is the number of steps taken."""
+    e = A.Ensemble.from_dump(os.path.join(GOLDEN, "c4_dynamic3_euv_init.bin"), ncols=2, lib=emu_lib)
+    assert e.execute(max_steps=10) == 10
+    assert list(e.status_all()["steps"]) == [10, 10]
+    assert e.execute(max_steps=3) == 3
+    assert list(e.status_all()["steps"]) == [13, 13]
