@@ -81,7 +81,7 @@ struct DevParams {
     int do_hydrodynamics;       // DO_HYDRO; 0 = no hydro stages until t > start_hydro_time (advection.cpp:62-64,139,170-200)
     double start_hydro_time;
     double avg_temperature_t0, avg_temperature_t1;
-    int last_kernel;            // 0 hydro, 1 friction, 2 radiation: who runs the step tail
+    int last_kernel;            // 0 hydro, 1 friction, 2 radiation, 3 photochemistry: who runs the step tail
     int tridiag_serial;         // 1: scalar J system solved in the reference's Thomas order on one lane (validation mode)
     // scalars
     double max_timestep_change, dt_min_init, dt_max, energy_epsilon, CFL_break_time;
@@ -92,6 +92,9 @@ struct DevParams {
     double kS_factor, kR_factor, kP_factor;       // const_opacity_{solar,rosseland,planck}_factor
     double T_int, core_cv, lT_spacing, photon_energy0;
     int num_plancks, h2_index;
+    // C2Ray photochemistry (photochem.cuh): number of ionising bands, Brent tolerances / iteration caps (ION_PRECISION, ...)
+    int num_he_bands, ion_maxiter, ion_heating_maxiter;
+    double ion_precision, ion_heating_precision;
     // shared geometry [NP]
     const double *x_i, *x_i12, *x_iVC, *dx, *surf, *vol, *omegaplus, *omegaminus, *spp_left, *spp_right;
     // shared tables

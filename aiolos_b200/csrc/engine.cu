@@ -10,6 +10,7 @@
 #include "rad_simple.cuh"
 #include "rad_full.cuh"
 #include "rad_full2.h"
+#include "photochem.cuh"
 #include "cuda_check.h"
 #include "step2.cuh"
 #include <cmath>
@@ -90,7 +91,13 @@ static void check_supported(const Problem& q) {
     if (q.use_self_gravity && q.num_species > 1) fail("PARI_SELF_GRAV_SWITCH 1 with several species");
     if (q.rs_time > 0) fail("PARI_SMOOTHING_TIME > 0 (time-dependent potential)");
     if (q.K_zz_init != 0) fail("KZZ_INIT != 0");
-    if (q.photochemistry_level != 0) fail("PHOTOCHEM_LEVEL != 0 (SURVEY 8 f1: next)");
+    if (q.photochemistry_level != 0 && q.photochemistry_level != 1) fail("PHOTOCHEM_LEVEL " + std::to_string(q.photochemistry_level) + " (general chemistry)");
+    if (q.photochemistry_level == 1) {
+        if (q.num_species != 3) fail("PHOTOCHEM_LEVEL 1 needs exactly the three species H, H+, e- (photochem.cpp:447-476)");
+        if (q.use_rad_fluxes != 0) fail("PHOTOCHEM_LEVEL 1 together with PARI_USE_RADIATION != 0 (every shipped deck of that kind stops in the reference itself: unpinned)");
+        if (!(q.friction_solver > 0 || q.do_hydrodynamics)) fail("PHOTOCHEM_LEVEL 1 without the drag update");
+        if (!q.do_hydrodynamics || q.start_hydro_time > 0 || q.use_self_gravity) fail("PHOTOCHEM_LEVEL 1 with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity");
+    }
     if (q.use_drag_predictor_step) fail("PARI_SECONDORDER_DRAG 1");
     if (q.use_total_pressure) fail("USE_TOTAL_PRESSURE 1");
     if (q.use_convective_fluxes) fail("USE_CONVECTION 1");
@@ -129,6 +136,7 @@ static std::string ensemble_mismatch(const Problem& a, const Problem& b) {
     CMP(photocooling_expansion); CMP(temperature_floor); CMP(max_temperature);
     CMP(const_opacity_solar_factor); CMP(const_opacity_rosseland_factor); CMP(const_opacity_planck_factor);
     CMP(R_star); CMP(T_star); CMP(T_int); CMP(core_cv); CMP(right_extrap_press_multiplier); CMP(max_mdot);
+    CMP(ion_precision); CMP(ion_heating_precision); CMP(ion_maxiter); CMP(ion_heating_maxiter);
     CMP(lT_spacing); CMP(avg_temperature_t0); CMP(avg_temperature_t1); CMP(num_plancks);
     CMP(x_i12); CMP(dx); CMP(vol); CMP(surf); CMP(l_i_in); CMP(l_i_out); CMP(photon_energies); CMP(planck_matrix);
     CMP(highenergy_switch); CMP(friction_coeff_mask); CMP(inv_totmasses); CMP(resonant_pair_matrix);
@@ -190,7 +198,11 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.avg_temperature_t0 = q0.avg_temperature_t0; p.avg_temperature_t1 = q0.avg_temperature_t1;
     // compute_drag_update (source.cpp:233-243): numeric solver whenever S > 1; the analytic one (0) only while hydro is on
     im->has_friction = S > 1 && (q0.friction_solver > 0 || (q0.friction_solver == 0 && q0.do_hydrodynamics));
-    p.last_kernel = q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
+    p.last_kernel = (q0.photochemistry_level == 1) ? 3 : q0.use_rad_fluxes ? 2 : (im->has_friction ? 1 : 0);
+    p.num_he_bands = 0;
+    if (q0.photochemistry_level > 0) for (int b = 0; b < q0.num_bands_in; b++) if (q0.l_i_in[b + 1] < 0.09116) p.num_he_bands++;   // init_and_bounds.cpp:390-398
+    p.ion_precision = q0.ion_precision; p.ion_heating_precision = q0.ion_heating_precision;
+    p.ion_maxiter = q0.ion_maxiter; p.ion_heating_maxiter = q0.ion_heating_maxiter;
     p.max_timestep_change = q0.max_timestep_change; p.dt_min_init = q0.dt_min_init; p.dt_max = q0.dt_max;
     p.energy_epsilon = q0.energy_epsilon; p.CFL_break_time = q0.CFL_break_time;
     p.right_extrap_press_multiplier = q0.right_extrap_press_multiplier; p.max_mdot = q0.max_mdot; p.planet_mass = q0.planet_mass;
@@ -333,7 +345,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
         p.dSband_top = im->upload(top);
     }
     p.Tsave = nullptr; p.cssave = nullptr;
-    if (im->has_friction && p.use_rad_fluxes) {
+    if (im->has_friction && (p.use_rad_fluxes || p.photochemistry_level == 1)) {
         p.Tsave = im->dalloc<double>((size_t)ncol * S * NP);
         p.cssave = im->dalloc<double>((size_t)ncol * S * NP);
     }
@@ -475,6 +487,7 @@ void Engine::launch_step() {
         }
         im->launches++;
     } else if (p.use_rad_fluxes == 1) { launch_full(); im->launches++; }
+    if (p.photochemistry_level == 1) { AIO_LAUNCH(k_photochem, (ncol + 4 * PHOTOCHEM_LANES - 1) / (4 * PHOTOCHEM_LANES), 128, 0, im->stream, p); im->launches++; }
     mark(3);
     if (prof) {
         CK(cudaEventSynchronize(im->prof_ev[3]));

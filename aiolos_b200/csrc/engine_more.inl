@@ -98,6 +98,7 @@ std::string Engine::kernel_name(int slot) const {
             if (im->full_mode == 2) return pre + "k_full_heat + k_full_asm2 + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
             return pre + "k_rad_full<" + std::to_string(im->full_mode == 0 ? 0 : (p.Bout + p.S + 7) / 8 * 8) + ">";
         }
+        if (p.photochemistry_level == 1) return pre + "k_photochem";
         if (p.use_rad_fluxes == 2) {
             if (im->fused && im->v2) return "";
             if (im->v2 && p.S == 1 && !p.Tsave && !p.kap_cell) return "k_rad3<" + cpt + ">";

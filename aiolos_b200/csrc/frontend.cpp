@@ -703,6 +703,8 @@ bool problem_from_files(const std::string& dir, const std::string& par_solo, con
         q.do_hydrodynamics = par.get<int>("DO_HYDRO", 1);
         q.start_hydro_time = par.get<double>("START_HYDRO_TIME", -1.);
         q.photochemistry_level = par.get<int>("PHOTOCHEM_LEVEL", 0);
+        q.ion_precision = par.get<double>("ION_PRECISION", 1e-12); q.ion_heating_precision = par.get<double>("ION_HEATING_PRECISION", 1e-12);
+        q.ion_maxiter = par.get<int>("ION_MAXITER", 128); q.ion_heating_maxiter = par.get<int>("ION_HEATING_MAXITER", 128);
         q.temperature_floor = par.get<double>("TEMPERATURE_FLOOR", 0.);
         q.max_temperature = par.get<double>("TEMPERATURE_MAX", 9e99);
         q.use_total_pressure = par.get<int>("USE_TOTAL_PRESSURE", 0);

@@ -57,6 +57,7 @@ struct Problem {                         // mirrors c_Sim (aiolos.h:361-828)
     std::vector<double> solar_heating_thermal;       // black-body part of the band fluxes (init_and_bounds.cpp:808-826)
     int fluxfile_used = 0;
     double T_star = 0, T_int = 0, T_planet = 0, core_cv = 0, right_extrap_press_multiplier = 1, max_mdot = -1;
+    double ion_precision = 1e-12, ion_heating_precision = 1e-12; int ion_maxiter = 128, ion_heating_maxiter = 128;   // C2Ray Brent solves
     double lT_spacing = 1, init_J_factor = -1, init_T_temp = 1, avg_temperature_t0 = 1e99, avg_temperature_t1 = 1e99;
     // grid (init_and_bounds.cpp:421-590)
     std::vector<double> x_i, x_i12, x_iVC, dx, surf, vol, omegaplus, omegaminus;

@@ -72,6 +72,14 @@ CASES = {
     # the shipped deck itself, unmodified (4002 cells): plugin + long column; only the 300-step state is kept (no init dump:
     # plugin decks are created from files)
     "p2_dusty_wind_full": ("PBC_model/", "dusty_wind.par", "silicate.spc", [300], "dusty_wind", "noinit"),
+    # the shipped C2Ray deck c2ray/hd209458b_xrays_dynamicGreyHeating_3s2b.par (atomic H, protons, electrons; PARI_USE_RADIATION 0)
+    # with the ion / electron start fractions of its species file raised from 1e-30 to 1e-6 (our variant mix_xrays_ions1e-6.spc:
+    # with 1e-30 the unmodified reference stops in its first step, "Root must be bracketed", because the proton density
+    # underflows to 0 and the heat-exchange matrix becomes infinite).  h0: the same with PHOTOCHEM_LEVEL 0 -- three charged /
+    # neutral species through the numeric friction solver with the physical collision model (i-n, e-n, i-e classes).
+    "h0_hd209458b_nophotochem": ("c2ray/", "hd209458b_nophotochem.par", "mix_xrays_ions1e-6.spc", [1, 100, 1000]),
+    # h1: PHOTOCHEM_LEVEL 1, the C2Ray ionisation + heating sweep (photochem.cpp:430-818)
+    "h1_hd209458b_c2ray": ("c2ray/", "hd209458b_xrays_dynamicGreyHeating_3s2b.par", "mix_xrays_ions1e-6.spc", [1, 100, 400, 800]),
 }
 
 KEEP_FINAL = ("dt_sequence", "t_max", "t_max_deck", "steps", "globalTime", "dt", "cflfactor", "timestep_rad2", "cfl_step",
@@ -87,6 +95,7 @@ def run_case(name):
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "test_files", f)], check=True)
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "runs_mdot_vs_euv_plot", f)], check=True)
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "PBC_model", f)], check=True)
+        subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "c2ray", f)], check=True)
     for k in steps:
         out = os.path.join(RUN, f"{name}_k{k}")
         cmd = [dump, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]

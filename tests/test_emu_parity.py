@@ -23,6 +23,10 @@ CASES = [
     ("t1_planetheating", 100, 1e-8),
     ("f4_friction_10spc_mild", 100, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8),
+    # H / H+ / e-: the ion-neutral, electron-neutral and ion-electron collision classes of the physical collision model (h0), and
+    # the C2Ray photoionisation + heating sweep on top (h1, PHOTOCHEM_LEVEL 1)
+    ("h0_hd209458b_nophotochem", 1, 1e-10), ("h0_hd209458b_nophotochem", 100, 1e-8),
+    ("h1_hd209458b_c2ray", 1, 1e-10), ("h1_hd209458b_c2ray", 100, 1e-8), ("h1_hd209458b_c2ray", 400, 1e-8),
 ]
 
 
@@ -35,6 +39,27 @@ def test_fields_match_reference(emu_lib, case, k, tol):
     errs = compare_with_golden(ens, ref)
     bad = {f: e for f, e in errs.items() if not e <= tol}
     assert not bad, f"{case} k={k}: {bad}"
+
+
+def photochem_late_regime(A_, lib):
+    """h1 at step 800: the neutral hydrogen has been ionised away (rho_H ~ 1e-9 of rho_p: the 1 - x of an ionisation fraction that
+    differs from 1 by less than its own rounding), its state is round-off noise in the reference as well and it is that noise which
+    sets dt through the energy limiter (dt falls from 3e-4 s to 4e-8 s between steps 400 and 600 in the reference itself).  What is
+    pinned there: the clock to the 1e-4 the neutral noise lets through, protons and electrons to 1e-6 (the two runs are not at the
+    same time any more), neutrals relative to the total hydrogen density."""
+    import numpy as np
+    ens, ref = run_case(A_, lib, "h1_hd209458b_c2ray", 800)
+    st = ens.status(0)
+    assert st["steps"] == 800 and st["state"] == 0
+    assert abs(st["t"] - ref["globalTime"][0]) <= 1e-4 * ref["globalTime"][0]
+    errs = compare_with_golden(ens, ref)
+    assert max(errs[f] for f in errs if f.startswith(("s1.", "s2."))) < 1e-6, errs
+    tot = ref["s0.u1"] + ref["s1.u1"]
+    assert np.max(np.abs(ens.get("u1", 0, 0) - ref["s0.u1"]) / tot) < 1e-10
+
+
+def test_photochem_late_regime(emu_lib):
+    photochem_late_regime(A, emu_lib)
 
 
 def test_c4_cfl_regime_thomas_order(emu_lib):

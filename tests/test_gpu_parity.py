@@ -27,6 +27,10 @@ CASES = [
     ("f4_friction_10spc_mild", 100, 1e-8), ("f4_friction_10spc_mild", 1000, 1e-8),
     ("g1_saturn_selfgrav2", 100, 1e-8), ("g1_saturn_selfgrav2", 400, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8), ("c7_dynamic3_tabulated", 1000, 1e-8),
+    # H / H+ / e-: the ion-neutral, electron-neutral and ion-electron collision classes of the physical collision model (h0), and
+    # the C2Ray photoionisation + heating sweep on top (h1, PHOTOCHEM_LEVEL 1)
+    ("h0_hd209458b_nophotochem", 1, 1e-10), ("h0_hd209458b_nophotochem", 100, 1e-8), ("h0_hd209458b_nophotochem", 1000, 1e-8),
+    ("h1_hd209458b_c2ray", 1, 1e-10), ("h1_hd209458b_c2ray", 100, 1e-8), ("h1_hd209458b_c2ray", 400, 1e-8),
 ]
 
 
@@ -52,6 +56,11 @@ def test_fields_match_reference(lib, case, k, tol):
     bad = {f: e for f, e in errs.items() if not e <= tol}
     assert not bad, f"{case} k={k}: {bad}"
     assert ens.kernel_launches >= 1
+
+
+def test_photochem_late_regime(lib):
+    from test_emu_parity import photochem_late_regime
+    photochem_late_regime(A, lib)
 
 
 def test_c4_cfl_regime(lib):
