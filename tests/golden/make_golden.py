@@ -72,6 +72,12 @@ CASES = {
     # the shipped deck itself, unmodified (4002 cells): plugin + long column; only the 300-step state is kept (no init dump:
     # plugin decks are created from files)
     "p2_dusty_wind_full": ("PBC_model/", "dusty_wind.par", "silicate.spc", [300], "dusty_wind", "noinit"),
+    # configs[0] with the wave driver switched on (WAVE_USE 1: add_wave() sets the momentum of the two left ghost cells every stage,
+    # init_and_bounds.cpp:1982-1987, advection.cpp:425-426; our variant -- the shipped wave decks test2/*wave*.par are unit-less
+    # legacy decks whose ghost cells hold cancellation noise, profiles/r1l_parity_sweep.md)
+    "w1_planet_wave": ("runs_searth/", "planet_spherical_wave.par", "mix3.spc", [1, 100, 1000]),
+    # configs[0] with the giantplanet boundary on the left (PARI_BOUND_TYPE_LEFT 5; our variant: no shipped deck selects it)
+    "gp1_planet_giantplanet": ("runs_searth/", "planet_spherical_giantplanet.par", "mix3.spc", [1, 100, 1000]),
     # the shipped C2Ray deck c2ray/hd209458b_xrays_dynamicGreyHeating_3s2b.par (atomic H, protons, electrons; PARI_USE_RADIATION 0)
     # with the ion / electron start fractions of its species file raised from 1e-30 to 1e-6 (our variant mix_xrays_ions1e-6.spc:
     # with 1e-30 the unmodified reference stops in its first step, "Root must be bracketed", because the proton density
@@ -96,6 +102,7 @@ def run_case(name):
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "runs_mdot_vs_euv_plot", f)], check=True)
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "PBC_model", f)], check=True)
         subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "c2ray", f)], check=True)
+        subprocess.run(["cp", os.path.join(HERE, "decks", f), os.path.join(RUN, "runs_searth", f)], check=True)
     for k in steps:
         out = os.path.join(RUN, f"{name}_k{k}")
         cmd = [dump, "-dir", d, "-par", par, "-nsteps", str(k), "-out", out]

@@ -23,6 +23,9 @@ CASES = [
     ("t1_planetheating", 100, 1e-8),
     ("f4_friction_10spc_mild", 100, 1e-8),
     ("c7_dynamic3_tabulated", 1, 1e-10), ("c7_dynamic3_tabulated", 100, 1e-8),
+    # the wave driver (add_wave, init_and_bounds.cpp:1982-1987) and the giantplanet boundary (:1882-1890) on configs[0]
+    ("w1_planet_wave", 1, 1e-10), ("w1_planet_wave", 100, 1e-8), ("w1_planet_wave", 1000, 1e-8),
+    ("gp1_planet_giantplanet", 1, 1e-10), ("gp1_planet_giantplanet", 100, 1e-8), ("gp1_planet_giantplanet", 1000, 1e-8),
     # H / H+ / e-: the ion-neutral, electron-neutral and ion-electron collision classes of the physical collision model (h0), and
     # the C2Ray photoionisation + heating sweep on top (h1, PHOTOCHEM_LEVEL 1)
     ("h0_hd209458b_nophotochem", 1, 1e-10), ("h0_hd209458b_nophotochem", 100, 1e-8),
