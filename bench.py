@@ -275,6 +275,22 @@ def main():
         return {"value": sm[1] * N_ * S_ / mx[0], "unit": "updates/s", "h2d_bytes_per_step": int(u_host.numel() * 8),
                 "d2h_bytes_per_step": int(nc * 8 + nc * (8 + 8 + 8 + 4)), "steps": nsteps}
 
+    def h2d_ceiling(nbytes, reps=8):
+        """Platform ceiling of the end-to-end leg: the same bytes per step as one plain pinned-host -> device cudaMemcpyAsync per
+        step (torch copy_, one copy per buffer) on this rank's GPU, all ranks at once, nothing else running.  Returns GB/s of this
+        rank's copies (max-over-ranks time)."""
+        h = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+        d = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+        d.copy_(h, non_blocking=True); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        mx, _ = reduce_max_sum([time.perf_counter() - t0])
+        del h, d
+        return nbytes * reps / mx[0] / 1e9
+
     ncols, n_total = args.ncols, args.ncols * world
     ens = build_sweep(ncols, n_total)
     N, S = ens.num_cells, ens.num_species
@@ -307,6 +323,14 @@ def main():
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------------
     e2e = e2e_leg(ens, args.e2e_steps)
     ens.close()
+    # how much of the platform's host -> device copy rate the end-to-end leg reaches (the upload of the state is what bounds it)
+    try:
+        gbs = h2d_ceiling(e2e["h2d_bytes_per_step"])
+        e2e["h2d_ceiling_gbs_per_gpu"] = gbs
+        e2e["ceiling_value"] = gbs * 1e9 / e2e["h2d_bytes_per_step"] * ncols * N * S * world     # updates/s if a step cost only its upload
+        e2e["frac_of_ceiling"] = e2e["value"] / e2e["ceiling_value"]
+    except Exception as ex:       # noqa: BLE001
+        e2e["h2d_ceiling_gbs_per_gpu"] = None; e2e["ceiling_note"] = str(ex)
 
     # ---- strong scaling: configs[4] as worded -- one 4096-column ensemble over the N GPUs -------------------------------------
     if world == 1 and ncols == STRONG_TOTAL:

@@ -93,3 +93,33 @@ def test_monitor_row_matches_reference(emu_lib, ref_run, tmp_path, par, S, monke
     assert np.all(np.abs(a[cs] - b[cs]) <= 2e-2 * np.abs(b[cs]))
     second = np.array([float(v) for v in mine[1][:ncol]])
     assert np.all(second[conv] == 0.0) and np.all(~np.isfinite(a[conv]))      # first row divides by the zero-initialised memory
+
+
+@pytest.mark.gpu
+def test_output_files_match_reference_gpu(product_lib, tmp_path, monkeypatch):
+    """The same comparison on the B200 through the product library.  The reference's files come from the prebuilt oracle binary
+    (oracle/_ref travels to the GPU box) run on the shipped input decks under decks/."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "aiolos_ref_dump")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/aiolos_ref_dump not built")
+    L = A.load_library(product_lib)
+    assert L.aio_device_count() > 0
+    run = str(tmp_path / "decks")
+    shutil.copytree(os.path.join(ROOT, "decks"), run)
+    par, stem, sp = "dynamic3_euv1e3_C_1s2b_rerun.par", "dynamic3_euv1e3_C_1s2b_rerun", "S1"
+    subprocess.run([exe, "-dir", "runs_mdot_vs_euv_plot/", "-par", par, "-nsteps", "700", "-out", os.path.join(run, "x")], cwd=run,
+                   stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    monkeypatch.chdir(run)
+    ens = A.Ensemble.from_files("runs_mdot_vs_euv_plot/", par, "", lib=product_lib)
+    ens.advance(700)
+    out = str(tmp_path) + "/"
+    ens.write_outputs(0, -1, out)
+    mine = _rows(os.path.join(out, f"output_{stem}_{sp}_t-1.dat"))
+    ref = _rows(os.path.join(run, "runs_mdot_vs_euv_plot", f"output_{stem}_{sp}_t-1.dat"))
+    assert len(ref[0]) == 23 and len(ref[1]) == 24 and len(ref[-1]) == 23
+    _cmp(mine, ref, [0, 1, 3, 10, 12, 19, 20, 22, 23], 1e-7, sp)
+    mine = _rows(os.path.join(out, f"diagnostic_{stem}_t-1.dat"))
+    ref = _rows(os.path.join(run, "runs_mdot_vs_euv_plot", f"diagnostic_{stem}_t-1.dat"))
+    _cmp(mine, ref, list(range(len(ref[0]) - 1)), 1e-6, "diagnostic")
+    ens.write_monitor(0, out, truncate=True)
+    assert os.path.exists(os.path.join(out, f"monitor_{stem}.dat"))
