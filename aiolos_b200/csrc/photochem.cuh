@@ -164,8 +164,8 @@ __device__ double brent_solve(double a, double b, const F& sys, double tol, int 
 
 // ---- the sweep: one thread per column ----------------------------------------------------------------------------------------------
 // Only PHOTOCHEM_LANES lanes of every warp carry a column: the sweep is one long dependent chain per thread, so what hides its
-// latency is the number of resident warps, not the number of busy lanes (4096 columns: 1024 warps instead of 128).
-constexpr int PHOTOCHEM_LANES = 4;
+// latency is the number of resident warps, not the number of busy lanes (4096 columns: 512 warps, one per SM sub-partition, instead of 128; measured r2: 57 ms per step with 32 lanes per warp, 61 ms with 4 -- the sweep is bound by its ~60 k instructions per cell, six pow() and two exp() per evaluation of the cooling function inside Brent).
+constexpr int PHOTOCHEM_LANES = 8;
 __global__ void __launch_bounds__(128) k_photochem(DevParams p) {
     const int lane = threadIdx.x & 31;
     if (lane >= PHOTOCHEM_LANES) return;

@@ -16,9 +16,10 @@ ap.add_argument("--ncols", type=int, default=4096)
 ap.add_argument("--spinup", type=int, default=600)
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--bytes", type=float, default=0.0, help="algorithmic bytes per cell-species-update (SURVEY 8d)")
+ap.add_argument("--lib", default=None, help="path of an alternative build of the library")
 ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
 a = ap.parse_args()
-ens = A.Ensemble.from_dump(os.path.join(ROOT, "tests", "golden", f"{a.case}_init.bin"), ncols=a.ncols)
+ens = A.Ensemble.from_dump(os.path.join(ROOT, "tests", "golden", f"{a.case}_init.bin"), ncols=a.ncols, lib=a.lib)
 for kv in a.opt:
     k_, v_ = kv.split("=", 1)
     ens.set_option(k_, v_)
