@@ -44,6 +44,33 @@ def test_fields_match_reference(emu_lib, case, k, tol):
     assert not bad, f"{case} k={k}: {bad}"
 
 
+def shipped_friction_deck_100_steps(A_, lib):
+    """BASELINE configs[1] as shipped (test_files/friction_6spc.par), 100 steps.  The deck starts at T ~ 1e-8 K where alpha*dt ~ 1e14
+    and is not reproducible by the reference itself: built without FMA contraction (fixture c2_friction_6spc_nofma_k100, made with
+    -ffp-contract=off) the unmodified reference produces NaN momenta and soft-crashes at step 98, built with it (the oracle
+    build) it reaches step 100, and the two dt sequences differ by O(1).  What can be held: densities bit for bit (friction does
+    not touch them, the periodic hydro step is the same), a finite state, no crash, and momenta that stay equal across species
+    as the stiff coupling demands."""
+    import os
+    import numpy as np
+    from aiodump import read_dump
+    from parity import GOLDEN
+    ens, ref = run_case(A_, lib, "c2_friction_6spc", 100)
+    st = ens.status(0)
+    assert st["steps"] == 100 and st["state"] == 0
+    nofma = read_dump(os.path.join(GOLDEN, "c2_friction_6spc_nofma_k100.bin"))
+    assert int(nofma["steps"][0]) == 98 and not np.isfinite(nofma["s0.u2"]).all()       # the reference against itself
+    for s in range(ens.num_species):
+        assert np.array_equal(ens.get("u1", 0, s), ref[f"s{s}.u1"])
+        assert np.isfinite(ens.get("u2", 0, s)).all() and np.isfinite(ens.get("u3", 0, s)).all()
+    v = np.array([ens.get("speed", 0, s)[5] for s in range(ens.num_species)])
+    assert np.ptp(v) <= 1e-9 * abs(np.mean(v))
+
+
+def test_shipped_friction_deck_100_steps(emu_lib):
+    shipped_friction_deck_100_steps(A, emu_lib)
+
+
 def photochem_late_regime(A_, lib):
     """h1 at step 800: the neutral hydrogen has been ionised away (rho_H ~ 1e-9 of rho_p: the 1 - x of an ionisation fraction that
     differs from 1 by less than its own rounding), its state is round-off noise in the reference as well and it is that noise which

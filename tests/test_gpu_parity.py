@@ -61,6 +61,11 @@ def test_fields_match_reference(lib, case, k, tol):
     assert ens.kernel_launches >= 1
 
 
+def test_shipped_friction_deck_100_steps(lib):
+    from test_emu_parity import shipped_friction_deck_100_steps
+    shipped_friction_deck_100_steps(A, lib)
+
+
 def test_photochem_late_regime(lib):
     from test_emu_parity import photochem_late_regime
     photochem_late_regime(A, lib)
