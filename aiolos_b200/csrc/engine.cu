@@ -36,7 +36,7 @@ struct Engine::Impl {
     // full FLD: 2 = register-tiled LU, four kernels (rad_full2.cuh; default when n <= 24); 0 = first-generation shared-memory
     // LU, one kernel (rad_full.cuh; option full_lu=smem, and n > 24); 1 = its shuffle-based register variant (full_lu=reg)
     int full_mode = 0;
-    bool full2_ok = false; size_t smem_full2 = 0; int full_ri = 0;
+    bool full2_ok = false; size_t smem_full2 = 0, smem_heat2 = 0; int full_ri = 0;
     bool fused = false;             // single-species persistent step kernel (k_step1)
     int step1_ctas = 3;             // resident CTAs per SM the fused kernel is compiled for (3: 80 registers, 2: 128)
     int steps_per_launch = 16;
@@ -612,6 +612,9 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         else if (value == "reg") im->full_mode = 1;
         else if (value == "tile") { if (!im->full2_ok) throw std::invalid_argument("option full_lu=tile: needs PARI_USE_RADIATION 1 with at most 24 unknowns per cell"); im->full_mode = 2; }
         else throw std::invalid_argument("option full_lu: expected 'tile', 'reg' or 'smem'");
+    } else if (key == "full_heat") {
+        if (value == "column") im->smem_heat2 = 0;           // k_full_heat (warp per column) instead of k_full_heat2
+        else throw std::invalid_argument("option full_heat: expected 'column'");
     } else if (key == "step1_ctas") {
         if (value != "2" && value != "3") throw std::invalid_argument("option step1_ctas: expected 2 or 3");
         im->step1_ctas = std::stoi(value);

@@ -57,14 +57,17 @@ void Engine::full_setup() {
         p.ssurf = im->dalloc<double>((size_t)p.ncol * p.Bin);
         im->full_ri = f2.RI;
         im->smem_full2 = (size_t)f2.sm_warp * sizeof(double);
-        full2_configure(im->full_ri, im->smem_full2);
+        // stellar heating by k_full_heat2 when its [Bin][N2+1] shared array leaves room for two CTAs per SM
+        im->smem_heat2 = ((size_t)p.Bin * ((p.N2 + 1) | 1) + p.Bin) * sizeof(double);
+        if (im->smem_heat2 > (size_t)maxsm / 2) im->smem_heat2 = 0;
+        full2_configure(im->full_ri, im->smem_full2, im->smem_heat2);
         im->full_mode = 2;
     }
 }
 void Engine::launch_full() {
     DevParams& p = im->p;
     if (im->full_mode == 2) {
-        full2_launch(p, im->full_ri, im->smem_full2, (void*)im->stream);
+        full2_launch(p, im->full_ri, im->smem_full2, im->smem_heat2, (void*)im->stream);
         im->launches += 3;
         return;
     }
@@ -95,7 +98,7 @@ std::string Engine::kernel_name(int slot) const {
     if (slot == 2) {
         std::string pre = p.kap_cell ? "k_opacity + " : "";
         if (p.use_rad_fluxes == 1) {
-            if (im->full_mode == 2) return pre + "k_full_heat + k_full_asm2 + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
+            if (im->full_mode == 2) return pre + (im->smem_heat2 ? "k_full_heat2" : "k_full_heat") + " + k_full_asm2 + k_full_lu<" + std::to_string(im->full_ri) + "> + k_full_post";
             return pre + "k_rad_full<" + std::to_string(im->full_mode == 0 ? 0 : (p.Bout + p.S + 7) / 8 * 8) + ">";
         }
         if (p.photochemistry_level == 1) return pre + "k_photochem";

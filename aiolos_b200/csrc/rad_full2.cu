@@ -2,19 +2,33 @@
 #define AIO_NO_SHARED_KERNELS
 #include "rad_full2.cuh"
 #include "cuda_check.h"
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 namespace aio {
 
-void full2_configure(int RI, size_t smem_lu) {
+void full2_configure(int RI, size_t smem_lu, size_t smem_heat2) {
+    if (smem_heat2) {
+        CK(cudaFuncSetAttribute(k_full_heat2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heat2));
+        CK(cudaFuncSetAttribute(k_full_heat2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heat2));
+        CK(cudaFuncSetAttribute(k_full_heat2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heat2));
+        CK(cudaFuncSetAttribute(k_full_heat2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_heat2));
+    }
     if (RI == 2) CK(cudaFuncSetAttribute(k_full_lu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
     else if (RI == 4) CK(cudaFuncSetAttribute(k_full_lu<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
     else CK(cudaFuncSetAttribute(k_full_lu<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lu));
 }
 
-void full2_launch(const DevParams& p, int RI, size_t smem_lu, void* stream_) {
+void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_heat2, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (smem_heat2) {
+        const int nt = std::min(512, (p.N2 + 31) / 32 * 32);          // one cell per thread where the column fits (no half-empty second pass)
+        if (p.S <= 1) AIO_LAUNCH(k_full_heat2<1>, p.ncol, nt, smem_heat2, stream, p);
+        else if (p.S <= 2) AIO_LAUNCH(k_full_heat2<2>, p.ncol, nt, smem_heat2, stream, p);
+        else if (p.S <= 4) AIO_LAUNCH(k_full_heat2<4>, p.ncol, nt, smem_heat2, stream, p);
+        else AIO_LAUNCH(k_full_heat2<16>, p.ncol, nt, smem_heat2, stream, p);
+    } else
     AIO_LAUNCH(k_full_heat, (p.ncol + 3) / 4, 128, 0, stream, p);
     {
         const unsigned grid = (unsigned)(((long long)p.ncol * p.N2 + 127) / 128);
@@ -49,7 +63,7 @@ void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, doub
         CK(cudaMemcpy(p.cs, cs.data(), cs.size() * sizeof(ColState), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p.fcoef, coef, n_coef * 8, cudaMemcpyHostToDevice));
         const size_t smem_lu = (size_t)fd.sm_warp * sizeof(double);
-        full2_configure(fd.RI, smem_lu);
+        full2_configure(fd.RI, smem_lu, 0);
         cudaStream_t stream = nullptr;
         if (fd.RI == 2) AIO_LAUNCH(k_full_lu<2>, ncols, 32, smem_lu, stream, p);
         else if (fd.RI == 4) AIO_LAUNCH(k_full_lu<4>, ncols, 32, smem_lu, stream, p);

@@ -139,6 +139,87 @@ __global__ void __launch_bounds__(128) k_full_heat(DevParams p) {
     if (lane < S) p.dS[idx_s(p, col, lane, 0)] = 0.;
 }
 
+// ---- stellar heating, parallel over cells (k_full_heat above walks the column with one lane per band: 273 dependent iterations of
+// exp / expm1, 0.66 ms at 4096 columns of configs[2]).  Only the optical-depth sum is sequential -- and must stay so, its
+// rounding order is the reference's (radiation.cpp:154-169) -- so it is the only thing done sequentially here: phase A, thread =
+// cell, cell optical depths into shared memory; phase B, thread = band, the running sum top-down (one dependent add per cell);
+// phase C, thread = cell, attenuation, heating and the per-species sums in band order.  Same expressions as k_full_heat; CTA =
+// column.  Needs Bin * (N2 + 1) doubles of shared memory; columns too long for that keep k_full_heat.
+template <int SMAX>
+__global__ void __launch_bounds__(512) k_full_heat2(DevParams p) {
+    AIO_DYN_SMEM(double, R);                       // [Bin][LDR] cell optical depth, then optical depth above the cell
+    const int col = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const ColState& cst = p.cs[col];
+    if (!cst.in_step) return;
+    const double tnow = cst.t;
+    const int N = p.N, N2 = p.N2, S = p.S, Bin = p.Bin;
+    const int LDR = (N2 + 1) | 1;
+    double* top_prev = R + (size_t)Bin * LDR;      // [Bin] dS_band(N, b) of the previous step
+    for (int b = tid; b < Bin; b += NT) top_prev[b] = p.dSband_top[(size_t)col * Bin + b];
+    for (int j = tid + 1; j <= N + 1; j += NT) {
+        const double dxj = __ldg(p.dx + j);
+        for (int b = 0; b < Bin; b++) {
+            double tot = 0;
+            for (int s = 0; s < S; s++) tot += kapv(p, col, s, b, j) * p.u[idx_u(p, 0, col, s, j)];
+            R[b * LDR + j] = tot * dxj;
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < Bin; b += NT) {
+        double rad_above = 0;
+        for (int j = N + 1; j > 0; j--) {
+            const double cell_tau = R[b * LDR + j];
+            R[b * LDR + j] = rad_above;
+            rad_above = (j == N + 1) ? 0. : rad_above + cell_tau;
+        }
+    }
+    __syncthreads();
+    for (int j = tid + 1; j <= N + 1; j += NT) {
+        const double dxj = __ldg(p.dx + j);
+        double acc[SMAX], rho[SMAX];
+#pragma unroll
+        for (int s = 0; s < SMAX; s++) { acc[s] = 0.; rho[s] = (s < S) ? p.u[idx_u(p, 0, col, s, j)] : 0.; }
+        for (int b = 0; b < Bin; b++) {
+            double F = p.solar_heating_final[(size_t)col * Bin + b];
+            if (tnow < p.radiation_rampup_time)
+                F = F * (p.init_radiation_factor + (1. - p.init_radiation_factor) * tnow / p.radiation_rampup_time);
+            const double rad_above = R[b * LDR + j];
+            double tot = 0;
+#pragma unroll
+            for (int s = 0; s < SMAX; s++) if (s < S) tot += kapv(p, col, s, b, j) * rho[s];
+            const double cell_tau = tot * dxj;
+            const double rad_j = (j == N + 1) ? 0. : rad_above + cell_tau;
+            double dSb;
+            if (j < N + 1) {
+                const double Sb = F * exp(-rad_above);
+                if (j == p.ng - 1) p.ssurf[(size_t)col * Bin + b] = Sb;
+                dSb = 0.25 * Sb / dxj * (1. - p.bond_albedo);
+                const double dtau_tot = -(rad_above - rad_j);
+                double dS_he = dSb;
+                if (dtau_tot > 1e-3) dSb *= (-expm1(-dtau_tot));
+                else dSb *= (-fastexpm1_2(-dtau_tot));
+                dS_he *= -fastexpm1_2(-0.);
+                dSb -= dS_he;
+                dSb = smax(dSb, 0.);
+            } else {
+                dSb = top_prev[b];
+            }
+            if (j == N) p.dSband_top[(size_t)col * Bin + b] = dSb;
+#pragma unroll
+            for (int s = 0; s < SMAX; s++)
+                if (s < S) {
+                    const double hsw = p.highenergy_switch[s * Bin + b];
+                    const double frac = hsw * kapv(p, col, s, b, j) * rho[s] * dxj / cell_tau;
+                    acc[s] += hsw * dSb * frac;               // reset_dS + the band sum, in band order
+                    if (acc[s] < 1e-50) acc[s] = 0.;
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < SMAX; s++) if (s < S) p.dS[idx_s(p, col, s, j)] = acc[s];
+    }
+    for (int s = tid; s < S; s += NT) p.dS[idx_s(p, col, s, 0)] = 0.;
+}
+
 // one record of the coefficient stream: `len` doubles (a multiple of 4) as 16-byte stores, i.e. whole 32-byte sectors
 template <int NMAX>
 __device__ __forceinline__ void store_record(double* dst, const double (&rec)[NMAX], int len) {

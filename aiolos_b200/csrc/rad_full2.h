@@ -62,8 +62,8 @@ __host__ __device__ inline Full2Dims full2_dims(int Bout, int S) {
 #ifndef FULL_LU_CTAS_PER_SM
 #define FULL_LU_CTAS_PER_SM 16        // resident single-warp CTAs per SM k_full_lu is compiled for (128 registers)
 #endif
-void full2_configure(int RI, size_t smem_lu);
-void full2_launch(const DevParams& p, int RI, size_t smem_lu, void* stream);
+void full2_configure(int RI, size_t smem_lu, size_t smem_heat2);
+void full2_launch(const DevParams& p, int RI, size_t smem_lu, size_t smem_heat2, void* stream);     // smem_heat2 = 0: k_full_heat
 
 void full2_selftest(int ncols, int N2, int Bout, int S, const double* coef, double* x);
 

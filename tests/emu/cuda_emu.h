@@ -24,6 +24,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __managed__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __restrict__
