@@ -121,6 +121,26 @@ def run_case(name):
         print(f"{name}: k={k} t={fin['globalTime'][0]:.6e} dt={fin['dt'][0]:.6e}")
 
 
+def run_nofma():
+    """configs[1] as shipped with the reference built WITHOUT FMA contraction (`make -C oracle nofma`): the reference's own
+    scatter on that deck (README.md in this directory)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "nofma", "aiolos_ref_dump")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "nofma"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["bash", os.path.join(ROOT, "oracle", "make_rundir.sh"), RUN], check=True, stdout=subprocess.DEVNULL)
+    for k in (100, 1000):
+        out = os.path.join(RUN, f"c2nofma_k{k}")
+        subprocess.run([exe, "-dir", "test_files/", "-par", "friction_6spc.par", "-spc", "friction_6spc.spc", "-nsteps", str(k), "-out", out],
+                       cwd=RUN, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT, check=True)
+        fin = read_dump(out + "_final.bin")
+        keep = {key: v for key, v in fin.items() if key in ("dt_sequence", "steps", "globalTime", "dt")
+                or (key[0] == "s" and "." in key and key.split(".", 1)[1] in ("u1", "u2", "u3", "sound_speed"))}
+        write_dump(os.path.join(HERE, f"c2_friction_6spc_nofma_k{k}.bin"), keep)
+        print(f"c2_friction_6spc (no FMA contraction): k={k} steps={int(fin['steps'][0])} t={fin['globalTime'][0]:.6e}")
+
+
 if __name__ == "__main__":
     for c in (sys.argv[1:] or list(CASES)):
-        run_case(c)
+        if c == "nofma":
+            run_nofma()
+        else:
+            run_case(c)
