@@ -273,7 +273,8 @@ __device__ __forceinline__ void friction_phase(const DevParams& p, const int col
 }
 
 #ifndef FRICTION_MIN_CTAS
-#define FRICTION_MIN_CTAS 4            // 128 registers (some spills) and 4 CTAs per SM: 0.67 -> 0.52 ms for 4096 x 102 cells x 6 species (r2)
+#define FRICTION_MIN_CTAS 4            // 128 registers (some spills) and 4 CTAs per SM: 0.67 -> 0.52 ms for 4096 x 102 cells x 6 species (r2;
+                                      // 1 / 3 / 4 / 5 / 6 CTAs: 0.67 / 0.57 / 0.52 / 0.63 / 0.61 ms)
 #endif
 template <int SS>
 __global__ void __launch_bounds__(128, FRICTION_MIN_CTAS) k_friction(DevParams p) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # k_friction<6> at 1 / 3 / 4 resident CTAs per SM (launch bounds): time the 6-species friction deck with each build.
 OUT=gpurun_out; mkdir -p $OUT
-for v in "" _f3 _f4; do
+for v in "" _f3 _f4 _f5 _f6; do
   lib=aiolos_b200/libaiolos_b200$v.so
   [ -f $lib ] || continue
   echo "== $lib"
