@@ -124,10 +124,12 @@ struct C2RayHeat {
 };
 
 // ---- Brent's method, brent.h:15-109.  status: 0 ok, 1 root not bracketed, 2 no convergence (the reference throws) -------------------
+// (fa0, fb0: sys(a), sys(b) when the caller has just evaluated them -- same arguments, same values, two evaluations saved)
 template <class F>
-__device__ double brent_solve(double a, double b, const F& sys, double tol, int max_iter, int& status) {
-    double fa = sys(a);
-    double fb = sys(b);
+__device__ double brent_solve(double a, double b, const F& sys, double tol, int max_iter, int& status, bool have = false, double fa0 = 0,
+                              double fb0 = 0) {
+    double fa = have ? fa0 : sys(a);
+    double fb = have ? fb0 : sys(b);
     status = 0;
     if (!(fa * fb <= 0)) { status = 1; return b; }
     const double EPS = 2.220446049250313e-16;
@@ -245,18 +247,20 @@ __global__ void __launch_bounds__(128) k_photochem(DevParams p) {
             {
                 C2RayHeat heat(GammaH - dEk / (dt + 1e-300), dt, nX_new, TX, (ion.R + ion.B * ne) * ne * ne,
                                (ion.C * ne + ion.photoionization_rate(x_bar)) * nH);
-                double Te1 = TX[2], Te2;
-                if (heat(Te1) < 0) {
-                    Te2 = Te1; Te1 = Te2 / 1.4;
+                // bracket the temperature (photochem.cpp:624-639); h1 / h2 follow heat(Te1) / heat(Te2) so that Brent does not
+                // evaluate them again
+                double Te1 = TX[2], Te2, h1 = heat(Te1), h2;
+                if (h1 < 0) {
+                    Te2 = Te1; h2 = h1; Te1 = Te2 / 1.4;
                     int guard = 0;
-                    while (heat(Te1) < 0 && ++guard < 4096) { Te2 = Te1; Te1 /= 1.4; }
+                    while ((h1 = heat(Te1)) < 0 && ++guard < 4096) { Te2 = Te1; h2 = h1; Te1 /= 1.4; }
                 } else {
                     Te2 = Te1 * 1.4;
                     int guard = 0;
-                    while (heat(Te2) > 0 && ++guard < 4096) { Te1 = Te2; Te2 *= 1.4; }
+                    while ((h2 = heat(Te2)) > 0 && ++guard < 4096) { Te1 = Te2; h1 = h2; Te2 *= 1.4; }
                 }
                 int st;
-                const double Te = brent_solve(Te1, Te2, heat, p.ion_heating_precision, p.ion_heating_maxiter, st);
+                const double Te = brent_solve(Te1, Te2, heat, p.ion_heating_precision, p.ion_heating_maxiter, st, true, h1, h2);
                 if (st != 0) fail = 1;                             // the reference throws here and ends the run
                 heat.compute_T(Te, Tnew);
             }
