@@ -112,6 +112,7 @@ struct DevParams {
     // per-column hydrostatic offsets and gravity source coefficient [ncol][S][NP]
     const double *g_cF, *g_cB, *g_idxF, *g_idxB, *g_wl, *g_wr, *g_ivol, *g_idx;
     double *dpm, *dpp, *gsrc;
+    double *kzzf; double kzz;           // KZZ_INIT != 0: K_zzf per species and cell [ncol][S][NP] (source.cpp:174-219), refreshed every step; else null
     // per-cell opacities for the models that depend on the local state (T, K, D): [ncol][S][Bin+2*Bout][NP], filled by k_opacity
     // before the radiation kernel (the reference's update_opacities pass); null for the constant models C and P
     double *kap_cell;

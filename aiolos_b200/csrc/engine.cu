@@ -90,7 +90,7 @@ static void check_supported(const Problem& q) {
     if (q.num_cells < 6) fail("fewer than 6 cells");
     if (q.use_self_gravity && q.num_species > 1) fail("PARI_SELF_GRAV_SWITCH 1 with several species");
     if (q.rs_time > 0) fail("PARI_SMOOTHING_TIME > 0 (time-dependent potential)");
-    if (q.K_zz_init != 0) fail("KZZ_INIT != 0");
+    if (q.K_zz_init != 0 && (q.use_self_gravity || q.photochemistry_level != 0)) fail("KZZ_INIT != 0 together with self-gravity or photochemistry");
     if (q.photochemistry_level != 0 && q.photochemistry_level != 1) fail("PHOTOCHEM_LEVEL " + std::to_string(q.photochemistry_level) + " (general chemistry)");
     if (q.photochemistry_level == 1) {
         if (q.num_species != 3) fail("PHOTOCHEM_LEVEL 1 needs exactly the three species H, H+, e- (photochem.cpp:447-476)");
@@ -335,6 +335,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     p.u = im->upload(hu); p.eint = im->upload(he); p.phi = im->upload(hphi); p.phis = im->upload(hphis);
     p.J = im->upload(hJ); p.solar_heating_final = im->upload(hsol); p.prim2v = im->upload(hp2); p.phiN = im->upload(hphiN);
     p.dS = im->dalloc<double>((size_t)ncol * S * NP);
+    p.kzz = q0.K_zz_init; p.kzzf = (q0.K_zz_init != 0) ? im->dalloc<double>((size_t)ncol * S * NP) : nullptr;
     p.dpm = im->dalloc<double>((size_t)ncol * S * NP); p.dpp = im->dalloc<double>((size_t)ncol * S * NP);
     p.gsrc = im->dalloc<double>((size_t)ncol * S * NP);
     {   // dS_band(N, b) as the constructor left it: the first update_dS copies it into cell N+1 (radiation.cpp:263-265)
@@ -369,7 +370,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     im->fused = (S == 1) && !im->has_friction && !p.kap_cell && (p.use_rad_fluxes == 0 || p.use_rad_fluxes == 2);
     for (auto& sp : q0.species) if (sp.boundary_left == 0 || sp.boundary_right == 0) im->fused = false;   // hooks flag errors through p.cs
     im->hydro_switch = (!q0.do_hydrodynamics || q0.start_hydro_time > 0);
-    if (im->hydro_switch || q0.use_self_gravity) { im->v2 = false; im->fused = false; }   // DO_HYDRO 0 / START_HYDRO_TIME: only the v1 kernels carry the switch
+    if (im->hydro_switch || q0.use_self_gravity || q0.K_zz_init != 0) { im->v2 = false; im->fused = false; }   // (K_zz: phi_s changes every step)   // DO_HYDRO 0 / START_HYDRO_TIME: only the v1 kernels carry the switch
     int maxsm = 0; CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     // work arrays that do not fit in one CTA's shared memory (long columns, or many species in the simple FLD kernel) go to HBM
     p.scratch = nullptr; p.scratch_stride = 0; p.scratch_hydro = p.scratch_rad = 0;
@@ -628,7 +629,7 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");
     } else if (key == "kernels") {
         if (value == "v1") im->v2 = false;
-        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch || im->p.use_self_gravity) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity run the v1 kernels"); im->v2 = true; }
+        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch || im->p.use_self_gravity || im->p.kzzf) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity / KZZ_INIT run the v1 kernels"); im->v2 = true; }
         else throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
         if (total_steps() != 0) throw std::invalid_argument("option kernels must be set before the first step");
     } else throw std::invalid_argument("unknown option '" + key + "'");

@@ -543,7 +543,20 @@ void construct_species(Sim& S, int si, const ParFile& par, const std::string& sp
     s.mass = d.mass_amu * amu;
     s.prim.assign(N2, AOSp()); s.primlast.assign(N2, AOSp());
     s.phi_s.assign(N2, 0.); s.K_zzf.assign(N2, 1.);
-    for (int i = 0; i < N2; i++) s.phi_s[i] = q.phi[i] * s.K_zzf[i];          // update_kzz_and_gravpot with K_zz = 0
+    {   // update_kzz_and_gravpot(species_index), source.cpp:174-219 (called by the species constructor, init_and_bounds.cpp:1162)
+        const double mu = S.sp[0].d.mass_amu, mi = d.mass_amu;
+        int homopause = 0;
+        if (si > 0 && mi > 1e-3 && q.K_zz_init != 0) {
+            for (int i = 0; i < N2; i++) {
+                const double n = S.sp[0].prim[i].number_density;
+                s.K_zzf[i] = (q.K_zz[i] * n < 1.) ? 1. : mu / mi;
+                if (i >= 1 && s.K_zzf[i] > 0.99999 && s.K_zzf[i - 1] < 0.99999) homopause = i;
+            }
+        }
+        for (int i = 0; i < N2; i++) s.phi_s[i] = q.phi[i] * s.K_zzf[i];
+        const double corr = (homopause == 0) ? 0. : q.phi[homopause] * (1. - mu / mi);
+        for (int i = 0; i < homopause; i++) s.phi_s[i] += corr;
+    }
     if (q.problem_number == 1) {
         double u1l = par.get<double>("PARI_INIT_DATA_U1L", 1.), u2l = par.get<double>("PARI_INIT_DATA_U2L", 0.), u3l = par.get<double>("PARI_INIT_DATA_U3L", 1.);
         double u1r = par.get<double>("PARI_INIT_DATA_U1R", 1.), u2r = par.get<double>("PARI_INIT_DATA_U2R", 0.), u3r = par.get<double>("PARI_INIT_DATA_U3R", 1.);

@@ -143,7 +143,8 @@ __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesCons
     case 1:  // open
         for (int i = ng; i > 0; i--) {
             Prim3 q = cons_to_prim(W.at(0, i), W.at(1, i), W.at(2, i), sc.gm1);
-            double dphi = (phi[i] * 1.0 - phi[i - 1] * 1.0) / (p.dx[i - 1] + p.dx[i]);
+            const double* kz = p.kzzf ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
+            double dphi = (phi[i] * (kz ? kz[i] : 1.0) - phi[i - 1] * (kz ? kz[i - 1] : 1.0)) / (p.dx[i - 1] + p.dx[i]);
             dphi *= (p.omegaplus[i] * p.dx[i] + p.omegaminus[i - 1] * p.dx[i - 1]);
             q.p = q.p + q.rho * dphi;
             q.p = smax(q.p, 0.0);
@@ -195,7 +196,8 @@ __device__ inline void apply_boundary_right(const DevParams& p, const SpeciesCon
     case 1:  // open
         for (int i = Ncell + ng; i < Ncell + 2 * ng; i++) {
             Prim3 q = cons_to_prim(W.at(0, i - 1), W.at(1, i - 1), W.at(2, i - 1), sc.gm1);
-            double dphi = (phi[i] * 1.0 - phi[i - 1] * 1.0) / (p.dx[i - 1] + p.dx[i]);
+            const double* kz = p.kzzf ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
+            double dphi = (phi[i] * (kz ? kz[i] : 1.0) - phi[i - 1] * (kz ? kz[i - 1] : 1.0)) / (p.dx[i - 1] + p.dx[i]);
             dphi *= (p.omegaplus[i] * p.dx[i] + p.omegaminus[i - 1] * p.dx[i - 1]);
             q.p = q.p - p.right_extrap_press_multiplier * q.rho * dphi;
             q.p = smax(q.p, 1e-1 * q.p);
@@ -337,7 +339,6 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
     double* Rr = Lp + N2;       double* Rv = Rr + N2;  double* Rp = Rv + N2;   // right edge states prim_r
     double* red = Rp + N2;                                                     // 32 doubles
     double* win = red + 32;                                                    // 3*4*ng doubles
-    (void)red;
     BndWin W; W.w = win; W.ng = ng; W.N2 = N2;
 
     // phi_s snapshot for all species before any BC edits phi (update_kzz_and_gravpot, advection.cpp:101-102 /
@@ -347,11 +348,40 @@ __device__ __forceinline__ void hydro_phase(const DevParams& p, const int col, d
         __syncthreads();
         self_gravity_update(p, col, Pr, Pv, Pp);
     }
-    if (snap || p.use_self_gravity) {
+    if (snap || p.use_self_gravity || p.kzzf) {
         const double* phi = p.phi + idx_c(p, col, 0);
         for (int s = 0; s < p.S; s++) {
             double* phis = p.phis + idx_s(p, col, s, 0);
-            for (int j = tid; j < N2; j += NT) phis[j] = phi_snapshot(p, col, phi, j) * 1.0;
+            if (!p.kzzf) {
+                for (int j = tid; j < N2; j += NT) phis[j] = phi_snapshot(p, col, phi, j) * 1.0;
+            } else {
+                // update_kzz_and_gravpot (source.cpp:174-219): below the homopause of the dominant species (species 0) a heavier
+                // species feels the potential scaled by mu / m_i, shifted so that phi_s is continuous at the homopause
+                double* kz = p.kzzf + idx_s(p, col, s, 0);
+                const double mu = p.sp[0].mass_amu, mi = p.sp[s].mass_amu;
+                const bool scaled = (s > 0 && mi > 1e-3);
+                const double one = 0.99999;
+                auto kzzf_at = [&](int i) -> double {
+                    if (!scaled) return 1.;
+                    const double n = p.u[idx_u(p, 0, col, 0, i)] / p.sp[0].mass;      // species[0].prim[i].number_density
+                    return (p.kzz * n < 1.) ? 1. : mu / mi;
+                };
+                double hmax = 0;
+                for (int j = tid; j < N2; j += NT) {
+                    const double k = kzzf_at(j);
+                    kz[j] = k;
+                    if (scaled && j >= 1 && k > one && kzzf_at(j - 1) < one) hmax = (double)j;     // the last such cell wins
+                }
+                hmax = block_max(hmax, red);
+                __syncthreads();
+                const int h = (int)hmax;
+                const double corr = (h == 0) ? 0. : phi_snapshot(p, col, phi, h) * (1. - mu / mi);
+                for (int j = tid; j < N2; j += NT) {
+                    double v = phi_snapshot(p, col, phi, j) * kz[j];
+                    if (j < h) v += corr;
+                    phis[j] = v;
+                }
+            }
         }
         __syncthreads();
     }

@@ -78,6 +78,9 @@ CASES = {
     "w1_planet_wave": ("runs_searth/", "planet_spherical_wave.par", "mix3.spc", [1, 100, 1000]),
     # configs[0] with the giantplanet boundary on the left (PARI_BOUND_TYPE_LEFT 5; our variant: no shipped deck selects it)
     "gp1_planet_giantplanet": ("runs_searth/", "planet_spherical_giantplanet.par", "mix3.spc", [1, 100, 1000]),
+    # c5 (two species, n-n friction, simple FLD + collisional heat exchange) with KZZ_INIT 1e-10 and a second species of 16 amu
+    # (our variant; no shipped deck sets KZZ_INIT): update_kzz_and_gravpot's homopause scaling of phi_s (source.cpp:174-219), every step
+    "z1_dynamic3_2spc_kzz": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_kzz.par", None, [1, 100, 1000]),
     # the shipped C2Ray deck c2ray/hd209458b_xrays_dynamicGreyHeating_3s2b.par (atomic H, protons, electrons; PARI_USE_RADIATION 0)
     # with the ion / electron start fractions of its species file raised from 1e-30 to 1e-6 (our variant mix_xrays_ions1e-6.spc:
     # with 1e-30 the unmodified reference stops in its first step, "Root must be bracketed", because the proton density

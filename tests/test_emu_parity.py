@@ -26,6 +26,8 @@ CASES = [
     # the wave driver (add_wave, init_and_bounds.cpp:1982-1987) and the giantplanet boundary (:1882-1890) on configs[0]
     ("w1_planet_wave", 1, 1e-10), ("w1_planet_wave", 100, 1e-8), ("w1_planet_wave", 1000, 1e-8),
     ("gp1_planet_giantplanet", 1, 1e-10), ("gp1_planet_giantplanet", 100, 1e-8), ("gp1_planet_giantplanet", 1000, 1e-8),
+    # KZZ_INIT != 0: the homopause scaling of the species potentials, recomputed every step (source.cpp:174-219)
+    ("z1_dynamic3_2spc_kzz", 1, 1e-10), ("z1_dynamic3_2spc_kzz", 100, 1e-8), ("z1_dynamic3_2spc_kzz", 1000, 1e-8),
     # H / H+ / e-: the ion-neutral, electron-neutral and ion-electron collision classes of the physical collision model (h0), and
     # the C2Ray photoionisation + heating sweep on top (h1, PHOTOCHEM_LEVEL 1)
     ("h0_hd209458b_nophotochem", 1, 1e-10), ("h0_hd209458b_nophotochem", 100, 1e-8),

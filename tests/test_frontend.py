@@ -20,6 +20,7 @@ DECKS = {   # case -> (deck dir, par, spc)
     "d1_dustywave_nonstiff": ("test_files/", "dustywave_nonstiff.par", "hydrogen.spc"),
     "c7_dynamic3_tabulated": ("runs_mdot_vs_euv_plot/", "dynamic3_tabulated.par", ""),
     "c5_dynamic3_2spc_collheat": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_collheat.par", ""),
+    "z1_dynamic3_2spc_kzz": ("runs_mdot_vs_euv_plot/", "dynamic3_2spc_kzz.par", ""),
     # self-gravity: the constructor relaxes the atmosphere in its own potential (50 x update_mass_and_pot + hydrostatic init)
     "g1_saturn_selfgrav2": ("runs_schulik2020/", "saturn_1grey_1s1b_selfgrav2.par", "mix_grey1e-2.spc"),
 }
