@@ -31,6 +31,7 @@ struct Engine::Impl {
     bool has_friction = false;
     bool big = false;               // 1024 threads per column and/or work arrays in HBM (long columns): v1 kernels only
     bool hydro_switch = false;      // deck runs (part of) its time with the hydro module off
+    bool v2_unavailable = false;    // the ctor had to switch v2 off (shared memory): option kernels=v2 must not switch it back on
     bool v2 = true;                 // second-generation kernels (step2.cuh); option kernels=v1 selects the line-by-line ones
     size_t smem_rad2 = 0, smem_rad3 = 0, smem_step1 = 0;
     // full FLD: 2 = register-tiled LU, four kernels (rad_full2.cuh; default when n <= 24); 0 = first-generation shared-memory
@@ -159,7 +160,14 @@ static std::string ensemble_mismatch(const Problem& a, const Problem& b) {
     return "";
 }
 
+// A constructor that throws (unsupported deck, factor storage that does not fit, ...) must not leave device memory, streams or
+// events behind: the caller may retry in the same process with fewer columns.
 Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
+    try { construct(cols, device); }
+    catch (...) { destroy(); throw; }
+}
+
+void Engine::construct(const std::vector<Problem>& cols, int device) {
     if (cols.empty()) throw std::runtime_error("empty ensemble");
     const Problem& q0 = cols[0];
     check_supported(q0);
@@ -394,7 +402,7 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     SETSM(k_step1<1>, im->smem_step1); SETSM(k_step1<2>, im->smem_step1); SETSM(k_step1<4>, im->smem_step1); SETSM(k_step1<8>, im->smem_step1);
     SETSM(k_hydro2<1>, im->smem_hydro); SETSM(k_hydro2<2>, im->smem_hydro); SETSM(k_hydro2<4>, im->smem_hydro); SETSM(k_hydro2<8>, im->smem_hydro);
     if (p.use_rad_fluxes == 2) {
-        if (im->smem_rad2 > (size_t)maxsm) { im->v2 = false; im->fused = false; }
+        if (im->smem_rad2 > (size_t)maxsm) { im->v2 = false; im->fused = false; im->v2_unavailable = true; }
         else {
             SETSM(k_rad3<1>, im->smem_rad3); SETSM(k_rad3<2>, im->smem_rad3); SETSM(k_rad3<4>, im->smem_rad3); SETSM(k_rad3<8>, im->smem_rad3);
             SETSM(k_rad2<1>, im->smem_rad2); SETSM(k_rad2<2>, im->smem_rad2); SETSM(k_rad2<4>, im->smem_rad2); SETSM(k_rad2<8>, im->smem_rad2);
@@ -411,7 +419,9 @@ Engine::Engine(const std::vector<Problem>& cols, int device) : im(new Impl) {
     CK(cudaStreamSynchronize(im->stream));
 }
 
-Engine::~Engine() {
+Engine::~Engine() { destroy(); }
+
+void Engine::destroy() {
     if (!im) return;
     for (void* q : im->allocs) cudaFree(q);
     if (im->pinned) cudaFreeHost(im->pinned);
@@ -421,6 +431,7 @@ Engine::~Engine() {
     if (im->copy_stream) { cudaStreamDestroy(im->copy_stream); cudaEventDestroy(im->ev_up); cudaEventDestroy(im->ev_free); }
     if (im->stream) cudaStreamDestroy(im->stream);
     delete im;
+    im = nullptr;
 }
 
 int Engine::ncol() const { return im->p.ncol; }
@@ -624,14 +635,15 @@ void Engine::set_option(const std::string& key, const std::string& value) {
         if (pct < 0 || pct > 100) throw std::invalid_argument("option carveout: expected 0..100");
         { auto kf = k_step1<4, 256>; CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); }
         { auto kf = k_step1<4, 256, 2>; CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); }
-    } else if (key == "fused") {
+    } else if (key == "fused") {             // 0: per-phase kernels instead of the persistent step kernel; 1 is the default where it applies
         if (value == "0") im->fused = false;
-        else if (value != "1") throw std::invalid_argument("option fused: expected 0 or 1");
+        else if (value == "1") { if (!im->fused) throw std::invalid_argument("option fused=1: the persistent step kernel does not apply to this deck (or was switched off)"); }
+        else throw std::invalid_argument("option fused: expected 0 or 1");
     } else if (key == "kernels") {
-        if (value == "v1") im->v2 = false;
-        else if (value == "v2") { if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch || im->p.use_self_gravity || im->p.kzzf) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity / KZZ_INIT run the v1 kernels"); im->v2 = true; }
-        else throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
+        if (value != "v1" && value != "v2") throw std::invalid_argument("option kernels: expected 'v1' or 'v2'");
         if (total_steps() != 0) throw std::invalid_argument("option kernels must be set before the first step");
+        if (value == "v1") im->v2 = false;
+        else if (value == "v2") { if (im->v2_unavailable) throw std::invalid_argument("option kernels=v2: the second-generation radiation kernel does not fit this deck's shared memory"); if (im->big) throw std::invalid_argument("option kernels=v2: long columns run the v1 kernels"); if (im->hydro_switch || im->p.use_self_gravity || im->p.kzzf) throw std::invalid_argument("option kernels=v2: decks with DO_HYDRO 0 / START_HYDRO_TIME / self-gravity / KZZ_INIT run the v1 kernels"); im->v2 = true; }
     } else throw std::invalid_argument("unknown option '" + key + "'");
 }
 long long Engine::total_steps() {

@@ -41,6 +41,8 @@ private:
     struct Impl;
     Impl* im;
     Problem prob0;
+    void construct(const std::vector<Problem>& columns, int device);
+    void destroy();
     void launch_step();
     void launch_fused(long long nsteps);
     void launch_friction();

@@ -114,8 +114,10 @@ int aio_problem_field(aio_ensemble* e, int column, const char* name, double* dst
 int aio_upload_state(aio_ensemble* e, const double* u_host);
 int aio_download_state(aio_ensemble* e, double* u_host);
 /* Pipelined variant: the copy from (pinned) host memory runs on a second stream into a staging buffer while earlier steps
- * are still executing; aio_commit_upload makes the staged state current (ordered on the device by events).  u_host must
- * stay valid and unchanged until the commit. */
+ * are still executing; aio_commit_upload makes the staged state current (ordered on the device by events: it does not wait on
+ * the host).  u_host must stay valid and unchanged until the next call that synchronises with the ensemble's stream
+ * (aio_advance, aio_status*, aio_column_mass, aio_download_state).  The first step after an upload still takes its dt from
+ * the CFL / energy-change numbers of the state that was replaced. */
 int aio_upload_state_async(aio_ensemble* e, const double* u_host);
 int aio_commit_upload(aio_ensemble* e);
 /* Sum over all columns/species/cells of u1 (mass per column, weighted by cell volume) -- a small result to read back. */

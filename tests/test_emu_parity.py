@@ -13,11 +13,11 @@ CASES = [
     ("c1_planet_spherical", 1, 1e-10), ("c1_planet_spherical", 100, 1e-8), ("c1_planet_spherical", 2000, 1e-8),
     ("c2m_friction_6spc_mild", 1, 1e-10), ("c2m_friction_6spc_mild", 100, 1e-8), ("c2m_friction_6spc_mild", 1000, 1e-8),
     ("c4_dynamic3_euv", 1, 1e-10), ("c4_dynamic3_euv", 100, 1e-8),
-    ("c3_searth_22b", 1, 1e-10), ("c3_searth_22b", 20, 1e-8),
+    ("c3_searth_22b", 1, 1e-10),          # 20 steps of c3 on the emulator: tests/test_frontend.py::test_files_to_k_steps (from the deck's files)
     ("c5_dynamic3_2spc_collheat", 1, 1e-10), ("c5_dynamic3_2spc_collheat", 100, 1e-8),
     ("c6_dynamic3_2spc_fullfld", 1, 1e-10), ("c6_dynamic3_2spc_fullfld", 100, 1e-8),
     ("d1_dustywave_nonstiff", 1, 1e-10), ("d1_dustywave_nonstiff", 100, 1e-8), ("d1_dustywave_nonstiff", 800, 1e-8),
-    ("n1_searth_nohydro", 1, 1e-10), ("n1_searth_nohydro", 100, 1e-8), ("n2_radtest_1s1b", 242, 1e-8),
+    ("n1_searth_nohydro", 1, 1e-10), ("n2_radtest_1s1b", 242, 1e-8),      # n1 at 100 / 300 steps: GPU table (28 s on the emulator)
     ("b1_hjwind_3054", 100, 1e-8), ("b2_dynamic3_3k", 100, 1e-8),
     ("f1_friction_2spc_an", 1, 1e-10), ("f1_friction_2spc_an", 500, 1e-8), ("f2_friction_2spc_phys_an", 500, 1e-8), ("f3_friction_3spc_an_mild", 1000, 1e-8),
     ("t1_planetheating", 100, 1e-8),
@@ -27,7 +27,7 @@ CASES = [
     ("w1_planet_wave", 1, 1e-10), ("w1_planet_wave", 100, 1e-8), ("w1_planet_wave", 1000, 1e-8),
     ("gp1_planet_giantplanet", 1, 1e-10), ("gp1_planet_giantplanet", 100, 1e-8), ("gp1_planet_giantplanet", 1000, 1e-8),
     # KZZ_INIT != 0: the homopause scaling of the species potentials, recomputed every step (source.cpp:174-219)
-    ("z1_dynamic3_2spc_kzz", 1, 1e-10), ("z1_dynamic3_2spc_kzz", 100, 1e-8), ("z1_dynamic3_2spc_kzz", 1000, 1e-8),
+    ("z1_dynamic3_2spc_kzz", 1, 1e-10), ("z1_dynamic3_2spc_kzz", 100, 1e-8),      # 1000 steps: GPU table
     # H / H+ / e-: the ion-neutral, electron-neutral and ion-electron collision classes of the physical collision model (h0), and
     # the C2Ray photoionisation + heating sweep on top (h1, PHOTOCHEM_LEVEL 1)
     ("h0_hd209458b_nophotochem", 1, 1e-10), ("h0_hd209458b_nophotochem", 100, 1e-8),
