@@ -291,14 +291,14 @@ def main():
         return {"value": regions[1], "unit": "updates/s", "h2d_bytes_per_step": int(u_host.numel() * 8),
                 "d2h_bytes_per_step": int(nc * 8 + nc * (8 + 8 + 8 + 4)), "steps": nsteps, "regions": regions}
 
-    def h2d_ceiling(nbytes, reps=12):
+    def h2d_ceiling(nbytes, reps=24):
         """Platform ceiling of the end-to-end leg: the same bytes as one step's upload, as plain pinned-host -> device
         cudaMemcpyAsync calls (torch copy_, one copy per buffer) on this rank's GPU while every other rank does the same and
         nothing else runs.  Each copy is timed with CUDA events; returns the best GB/s of the slowest rank."""
         h = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
         h.zero_()
         d = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
-        for _ in range(2):
+        for _ in range(6):
             d.copy_(h, non_blocking=True)
         torch.cuda.synchronize()
         barrier()
