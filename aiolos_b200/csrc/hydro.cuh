@@ -136,6 +136,8 @@ __device__ __forceinline__ void call_hook(const DevParams& p, const SpeciesConst
 }
 #endif
 
+// KZZ: the caller may run with KZZ_INIT != 0 (v1 kernels); the second-generation kernels never do and compile the K_zzf lookup out
+template <bool KZZ = true>
 __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W, double prim2_speed) {
     const int ng = p.ng;
     double* phi = p.phi + idx_c(p, col, 0);
@@ -143,7 +145,7 @@ __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesCons
     case 1:  // open
         for (int i = ng; i > 0; i--) {
             Prim3 q = cons_to_prim(W.at(0, i), W.at(1, i), W.at(2, i), sc.gm1);
-            const double* kz = p.kzzf ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
+            const double* kz = (KZZ && p.kzzf) ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
             double dphi = (phi[i] * (kz ? kz[i] : 1.0) - phi[i - 1] * (kz ? kz[i - 1] : 1.0)) / (p.dx[i - 1] + p.dx[i]);
             dphi *= (p.omegaplus[i] * p.dx[i] + p.omegaminus[i - 1] * p.dx[i - 1]);
             q.p = q.p + q.rho * dphi;
@@ -188,6 +190,7 @@ __device__ inline void apply_boundary_left(const DevParams& p, const SpeciesCons
     }
 }
 
+template <bool KZZ = true>
 __device__ inline void apply_boundary_right(const DevParams& p, const SpeciesConst& sc, int col, int s, BndWin& W) {
     const int ng = p.ng;
     const int Ncell = p.N - 2 * (ng - 1);
@@ -196,7 +199,7 @@ __device__ inline void apply_boundary_right(const DevParams& p, const SpeciesCon
     case 1:  // open
         for (int i = Ncell + ng; i < Ncell + 2 * ng; i++) {
             Prim3 q = cons_to_prim(W.at(0, i - 1), W.at(1, i - 1), W.at(2, i - 1), sc.gm1);
-            const double* kz = p.kzzf ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
+            const double* kz = (KZZ && p.kzzf) ? p.kzzf + idx_s(p, col, s, 0) : nullptr;      // K_zzf (1 without KZZ_INIT)
             double dphi = (phi[i] * (kz ? kz[i] : 1.0) - phi[i - 1] * (kz ? kz[i - 1] : 1.0)) / (p.dx[i - 1] + p.dx[i]);
             dphi *= (p.omegaplus[i] * p.dx[i] + p.omegaminus[i - 1] * p.dx[i - 1]);
             q.p = q.p - p.right_extrap_press_multiplier * q.rho * dphi;

@@ -162,14 +162,14 @@ __device__ __forceinline__ void hydro_stages_v2(const DevParams& p, const int co
         }
         __syncthreads();
         if (tid == 0) {
-            apply_boundary_left(p, sc, col, s, W, prim2_speed);
+            apply_boundary_left<false>(p, sc, col, s, W, prim2_speed);
             if (sc.use_wave == 1) {
                 const double tt = (stage == 0) ? t_old : t_old + dt;
                 W.at(1, 0) = W.at(0, 0) * sc.wave_amplitude * sin(12. * M_PI * tt / sc.wave_period);
                 W.at(1, 1) = W.at(1, 0);
             }
         }
-        if (tid == ((NT > 32) ? 32 : 0)) apply_boundary_right(p, sc, col, s, W);
+        if (tid == ((NT > 32) ? 32 : 0)) apply_boundary_right<false>(p, sc, col, s, W);
         __syncthreads();
         // ---- cons -> prim (eos.cpp:19-29) --------------------------------------------------------------------------------------
 #pragma unroll
